@@ -1,0 +1,281 @@
+"""
+Generate tests/golden/*.npz by running the UNMODIFIED reference (gnss-ins-sim,
+imported from /root/reference) in this container.  Test infrastructure only.
+
+    python oracle/gen_golden.py            # writes tests/golden/
+
+What is frozen:
+  logged_{bosch,nxp}.npz    demo_free_integration_openimu.py semantics: logged IMU
+                            data, ref_frame=0, earth_rot=False, gravity from ini.txt.
+  seeded_90deg_rf{0,1}.npz  np.random.seed(12345); 'mid-accuracy'; run(2): the
+                            reference's own gyro/accel and its att/pos/vel.
+  philox_*.npz              the b2ins Philox normal stream (oracle_np.noise_normals)
+                            injected into the reference's np.random.randn call
+                            sequence; reference outputs + end-point error stats.
+  traj_*.npz                pathgen.path_gen output (true trajectory + ideal IMU).
+  allan.npz, psd.npz        allan.allan_var / time_series_from_psd known answers.
+
+The reference cannot travel to the GPU box, the .npz files do.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get('B2INS_REFERENCE', '/root/reference')
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+
+from gnss_ins_sim.sim import ins_sim, imu_model          # noqa: E402
+from gnss_ins_sim.pathgen import pathgen                  # noqa: E402
+from gnss_ins_sim.allan import allan                      # noqa: E402
+from gnss_ins_sim.psd import time_series_from_psd as ref_psd   # noqa: E402
+from demo_algorithms import free_integration              # noqa: E402
+import oracle_np as onp                                   # noqa: E402
+
+D2R = math.pi / 180
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+MOTION = os.path.join(REF, 'demo_motion_def_files')
+
+
+class RandnQueue:
+    """Stand-in for np.random.randn serving prepared arrays in call order."""
+
+    def __init__(self):
+        self.q = []
+        self.calls = []
+
+    def push(self, arr):
+        self.q.append(np.array(arr, dtype=np.float64))
+
+    def __call__(self, *shape):
+        self.calls.append(shape)
+        a = self.q.pop(0)
+        assert a.shape == tuple(shape), (a.shape, shape)
+        return a
+
+
+def read_ini(path_csv):
+    ini = np.genfromtxt(path_csv, delimiter=',', skip_header=1, max_rows=1)
+    ini[0] *= D2R
+    ini[1] *= D2R
+    ini[6:9] *= D2R
+    return ini
+
+
+def fresh_imu(accuracy):
+    # imu_model.IMU mutates module-level dicts when given a dict;
+    # only the string profiles are used here, which are read-only.
+    return imu_model.IMU(accuracy=accuracy, axis=6, gps=False)
+
+
+def err_dict(e, white_key):
+    return {'b': np.array(e['b']), 'b_drift': np.array(e['b_drift']),
+            'b_corr': np.array(e['b_corr']), white_key: np.array(e[white_key])}
+
+
+def collect(sim, R):
+    d = sim.dmgr
+    out = {
+        'time': d.time.data, 'ref_pos': d.ref_pos.data, 'ref_vel': d.ref_vel.data,
+        'ref_att': d.ref_att_euler.data, 'ref_accel': d.ref_accel.data,
+        'ref_gyro': d.ref_gyro.data,
+        'gyro': np.stack([d.gyro.data[i] for i in range(R)]),
+        'accel': np.stack([d.accel.data[i] for i in range(R)]),
+        'att': np.stack([d.att_euler.data['algo0_%d' % i] for i in range(R)]),
+        'pos': np.stack([d.pos.data['algo0_%d' % i] for i in range(R)]),
+        'vel': np.stack([d.vel.data['algo0_%d' % i] for i in range(R)]),
+    }
+    for name, ang in (('att_euler', True), ('pos', False), ('vel', False)):
+        st = d.get_error_stats(name, err_stats_start=-1, angle=ang, use_output_units=False)
+        for k in ('max', 'avg', 'std'):
+            out['stat_%s_%s' % (name, k)] = np.asarray(st[k])
+    return out
+
+
+def gen_logged(name):
+    log_dir = os.path.join(REF, 'demo_data_files', name) + '/'
+    ini = np.genfromtxt(log_dir + 'ini.txt', delimiter=',')
+    ini[0:2] *= D2R
+    ini[6:9] *= D2R
+    algo = free_integration.FreeIntegration(ini, earth_rot=False)
+    sim = ins_sim.Sim([100.0, 0.0, 0.0], log_dir, ref_frame=0, imu=None, algorithm=algo)
+    sim.run(1)
+    d = sim.dmgr
+    np.savez_compressed(os.path.join(OUT, 'logged_%s.npz' % name),
+                        fs=100.0, ref_frame=0, earth_rot=False, ini=ini,
+                        gyro=d.gyro.data[0], accel=d.accel.data[0],
+                        att=d.att_euler.data['algo0_0'], pos=d.pos.data['algo0_0'],
+                        vel=d.vel.data['algo0_0'])
+
+
+def gen_seeded(ref_frame):
+    csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
+    ini = read_ini(csv)
+    np.random.seed(12345)
+    imu = fresh_imu('mid-accuracy')
+    algo = free_integration.FreeIntegration(ini)
+    sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu, algorithm=algo)
+    sim.run(2)
+    out = collect(sim, 2)
+    np.savez_compressed(os.path.join(OUT, 'seeded_90deg_rf%d.npz' % ref_frame),
+                        fs=100.0, ref_frame=ref_frame, ini=ini, **out)
+
+
+def inject_stream(q, n, run_ids, seed, vib_acc=None, vib_gyro=None):
+    """Queue the b2ins normals in the reference's call order:
+    per run: acc GM x3 (n,3) [column i used], [acc vib x3 (n,)], acc white (n,3),
+             gyro GM x3, [gyro vib x3], gyro white."""
+    z = onp.noise_normals(n, run_ids, seed)
+    zva, zvg = onp.vib_normals(n, run_ids, seed)
+    for r in range(len(run_ids)):
+        for gm, w, vib, zv in ((z['acc_gm'], z['acc_w'], vib_acc, zva),
+                               (z['gyr_gm'], z['gyr_w'], vib_gyro, zvg)):
+            for i in range(3):
+                blk = np.full((n, 3), np.nan)     # unused entries must never matter
+                blk[:, i] = gm[r, :, i]
+                q.push(blk)
+            if vib is not None and vib['type'] == 'random':
+                for i in range(3):
+                    q.push(zv[r, :, i])
+            q.push(w[r])
+
+
+def gen_philox(tag, motion, fs, accuracy, ref_frame, R, seed, env=None, run0=0):
+    csv = os.path.join(MOTION, motion)
+    ini = read_ini(csv)
+    imu = fresh_imu(accuracy)
+    algo = free_integration.FreeIntegration(ini)
+    sim = ins_sim.Sim([fs, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu, env=env,
+                      algorithm=algo)
+    # trajectory length is needed before the stream can be queued: run path_gen the
+    # way Sim does (it is deterministic), then run Sim with the queue installed.
+    probe = ins_sim.Sim([fs, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu, algorithm=None)
+    real_randn, real_rand = np.random.randn, np.random.rand
+    np.random.randn = lambda *s: np.zeros(s)
+    try:
+        probe.run(1)
+    finally:
+        np.random.randn = real_randn
+    n = probe.dmgr.time.data.shape[0]
+    run_ids = np.arange(run0, run0 + R)
+    vib_acc = vib_gyro = None
+    if env is not None:
+        vib_acc = sim._Sim__parse_env(env['acc']) if 'acc' in env else None
+        vib_gyro = sim._Sim__parse_env(env['gyro']) if 'gyro' in env else None
+    q = RandnQueue()
+    inject_stream(q, n, run_ids, seed, vib_acc, vib_gyro)
+    phases = onp.gyro_vib_phase_uniforms(run_ids, seed)
+    pq = [phases[r, c] for r in range(R) for c in range(3)]
+    np.random.randn = q
+    np.random.rand = lambda *s: np.array([pq.pop(0)])
+    try:
+        sim.run(R)
+    finally:
+        np.random.randn, np.random.rand = real_randn, real_rand
+    assert not q.q, 'unused queued normals: %d' % len(q.q)
+    out = collect(sim, R)
+    extra = {}
+    if env is not None:
+        for k, v in (('vib_acc', vib_acc), ('vib_gyro', vib_gyro)):
+            if v is not None:
+                extra[k + '_type'] = v['type']
+                extra[k + '_amp'] = np.array([v['x'], v['y'], v['z']])
+                extra[k + '_freq'] = v.get('freq', 0.0)
+    np.savez_compressed(os.path.join(OUT, 'philox_%s.npz' % tag),
+                        fs=fs, ref_frame=ref_frame, ini=ini, seed=seed, run_ids=run_ids,
+                        accuracy=accuracy,
+                        gyro_b=imu.gyro_err['b'], gyro_b_drift=imu.gyro_err['b_drift'],
+                        gyro_b_corr=imu.gyro_err['b_corr'], gyro_arw=imu.gyro_err['arw'],
+                        accel_b=imu.accel_err['b'], accel_b_drift=imu.accel_err['b_drift'],
+                        accel_b_corr=imu.accel_err['b_corr'], accel_vrw=imu.accel_err['vrw'],
+                        **out, **extra)
+
+
+def gen_traj(tag, motion, fs, ref_frame):
+    csv = os.path.join(MOTION, motion)
+    imu = fresh_imu('low-accuracy')
+    sim = ins_sim.Sim([fs, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu, algorithm=None)
+    real = np.random.randn
+    np.random.randn = lambda *s: np.zeros(s)
+    try:
+        sim.run(1)
+    finally:
+        np.random.randn = real
+    d = sim.dmgr
+    np.savez_compressed(os.path.join(OUT, 'traj_%s.npz' % tag), fs=fs, ref_frame=ref_frame,
+                        ini=read_ini(csv), time=d.time.data, ref_pos=d.ref_pos.data,
+                        ref_vel=d.ref_vel.data, ref_att=d.ref_att_euler.data,
+                        ref_accel=d.ref_accel.data, ref_gyro=d.ref_gyro.data)
+
+
+def gen_allan():
+    rng = np.random.RandomState(2024)
+    fs = 100.0
+    n = 180000
+    # white + random walk + a GM-like component: exercises all tau decades
+    x = 0.01 * rng.randn(n) + np.cumsum(1e-5 * rng.randn(n))
+    avar, tau = allan.allan_var(x, fs)
+    x2 = rng.randn(7351)       # ragged: n not a multiple of anything
+    avar2, tau2 = allan.allan_var(x2, 50.0)
+    x3 = rng.randn(800)        # too short: max_bin*ts < 1 -> ([], [])
+    a3, t3 = allan.allan_var(x3, 100.0)
+    assert len(a3) == 0
+    np.savez_compressed(os.path.join(OUT, 'allan.npz'), fs=fs, x=x, avar=avar, tau=tau,
+                        fs2=50.0, x2=x2, avar2=avar2, tau2=tau2, x3=x3)
+
+
+def gen_psd():
+    tab = np.genfromtxt(os.path.join(MOTION, 'vib_psd.csv'), delimiter=',', skip_header=1)
+    rng = np.random.RandomState(7)
+    out = {}
+    for tag, fs, n in (('a', 200.0, 1000), ('b', 200.0, 40001)):
+        half = 0.5 * fs
+        m = tab.shape[0]
+        if tab[-1, 0] > half:
+            m = np.where(tab[:, 0] > half)[0][0]
+        freq = tab[:m, 0].copy()
+        sxx = tab[:m, 1].copy()
+        N = n if n % 2 == 0 else n + 1
+        N = min(N, 16384)
+        L = N // 2 + 1
+        zn = rng.randn(L)
+        real = np.random.randn
+        np.random.randn = lambda *s: zn.copy()
+        try:
+            ok, x = ref_psd.time_series_from_psd(sxx.copy(), freq, fs, n)
+        finally:
+            np.random.randn = real
+        assert ok
+        out.update({'freq_' + tag: freq, 'sxx_' + tag: sxx, 'fs_' + tag: fs, 'n_' + tag: n,
+                    'z_' + tag: zn, 'x_' + tag: x})
+    np.savez_compressed(os.path.join(OUT, 'psd.npz'), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gen_logged('bosch')
+    gen_logged('nxp')
+    gen_seeded(0)
+    gen_seeded(1)
+    gen_philox('90deg_mid_rf1', 'motion_def-90deg_turn.csv', 100.0, 'mid-accuracy', 1, 8, 12345)
+    gen_philox('90deg_mid_rf0', 'motion_def-90deg_turn.csv', 100.0, 'mid-accuracy', 0, 8, 12345)
+    gen_philox('90deg_low_rf1_run1000', 'motion_def-90deg_turn.csv', 100.0, 'low-accuracy', 1, 4,
+               987654321987, run0=1000)
+    gen_philox('90deg_mid_rf1_vibrand', 'motion_def-90deg_turn.csv', 100.0, 'mid-accuracy', 1, 3,
+               777, env={'acc': '[0.03 0.001 0.01]-random', 'gyro': '[6 5 4]d-random'})
+    gen_philox('90deg_mid_rf0_vibsin', 'motion_def-90deg_turn.csv', 100.0, 'mid-accuracy', 0, 3,
+               778, env={'acc': '[0.03 0.001 0.01]g-3Hz-sinusoidal',
+                         'gyro': '[6 5 4]d-0.5Hz-sinusoidal'})
+    gen_traj('90deg_turn_100hz_rf1', 'motion_def-90deg_turn.csv', 100.0, 1)
+    gen_traj('90deg_turn_100hz_rf0', 'motion_def-90deg_turn.csv', 100.0, 0)
+    gen_allan()
+    gen_psd()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,123 @@
+"""Pin the NumPy oracle (oracle/oracle_np.py) against vectors produced by the
+unmodified reference (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import oracle_np as onp
+from conftest import load_golden, assert_close, wrap_pi
+
+TIGHT = 1e-12
+
+
+@pytest.mark.parametrize('name', ['bosch', 'nxp'])
+def test_logged_data_rf0(name):
+    g = load_golden('logged_%s.npz' % name)
+    att, pos, vel = onp.free_integration(0, float(g['fs']), g['gyro'][None], g['accel'][None],
+                                         g['ini'][None], earth_rot=False)
+    assert_close(att[0], g['att'], TIGHT, what='att')
+    assert_close(pos[0], g['pos'], TIGHT, what='pos')
+    assert_close(vel[0], g['vel'], TIGHT, what='vel')
+
+
+@pytest.mark.parametrize('rf', [0, 1])
+def test_seeded_reference_noise(rf):
+    g = load_golden('seeded_90deg_rf%d.npz' % rf)
+    ini = np.tile(g['ini'], (2, 1))
+    att, pos, vel = onp.free_integration(rf, float(g['fs']), g['gyro'], g['accel'], ini)
+    assert_close(att, g['att'], TIGHT, what='att')
+    assert_close(pos - pos[:, :1], g['pos'] - g['pos'][:, :1], TIGHT, what='pos-pos0')
+    assert_close(pos, g['pos'], TIGHT, what='pos')
+    assert_close(vel, g['vel'], TIGHT, what='vel')
+
+
+def _errs(g):
+    return ({'b': g['gyro_b'], 'b_drift': g['gyro_b_drift'], 'b_corr': g['gyro_b_corr'],
+             'arw': g['gyro_arw']},
+            {'b': g['accel_b'], 'b_drift': g['accel_b_drift'], 'b_corr': g['accel_b_corr'],
+             'vrw': g['accel_vrw']})
+
+
+def _vib(g, key):
+    if key + '_type' not in g:
+        return None
+    a = g[key + '_amp']
+    return {'type': str(g[key + '_type']), 'x': a[0], 'y': a[1], 'z': a[2],
+            'freq': float(g[key + '_freq'])}
+
+
+@pytest.mark.parametrize('tag', ['90deg_mid_rf1', '90deg_mid_rf0', '90deg_low_rf1_run1000',
+                                 '90deg_mid_rf1_vibrand', '90deg_mid_rf0_vibsin'])
+def test_philox_stream_through_reference(tag):
+    """oracle noise + mechanization + stats == reference fed the same normals."""
+    g = load_golden('philox_%s.npz' % tag)
+    ge, ae = _errs(g)
+    fs, rf = float(g['fs']), int(g['ref_frame'])
+    gyro, accel = onp.imu_noise(fs, g['ref_gyro'], g['ref_accel'], ge, ae, int(g['seed']),
+                                g['run_ids'], _vib(g, 'vib_acc'), _vib(g, 'vib_gyro'))
+    assert_close(gyro, g['gyro'], TIGHT, what='gyro')
+    assert_close(accel, g['accel'], TIGHT, what='accel')
+    R = gyro.shape[0]
+    att, pos, vel = onp.free_integration(rf, fs, gyro, accel, np.tile(g['ini'], (R, 1)))
+    assert_close(att, g['att'], 1e-10, what='att')
+    assert_close(pos, g['pos'], 1e-10, what='pos')
+    assert_close(vel, g['vel'], 1e-10, what='vel')
+    st = onp.end_point_error_stats(att, pos, vel, g['ref_att'], g['ref_pos'], g['ref_vel'])
+    for name in ('att_euler', 'pos', 'vel'):
+        for k in ('max', 'avg', 'std'):
+            assert_close(st[name][k], g['stat_%s_%s' % (name, k)], 1e-7, 1e-3,
+                         what='%s %s' % (name, k))
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 KAT from the Random123 distribution (kat_vectors):
+    ctr=0,key=0 ; ctr=ff..,key=ff.. ; ctr=pi digits,key=e digits... (first two)."""
+    x = onp.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in x] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xFFFFFFFF
+    x = onp.philox4x32_10(f, f, f, f, f, f)
+    assert [int(v) for v in x] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    x = onp.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(v) for v in x] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_normals_are_standard():
+    z0, z1 = onp.normal_pair(np.arange(200000), 0, 5, 42)
+    z = np.concatenate([z0, z1])
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3) < 0.06
+    assert abs(np.corrcoef(z0, z1)[0, 1]) < 0.01
+    assert np.isfinite(z).all()
+
+
+def test_allan_matches_reference():
+    g = load_golden('allan.npz')
+    avar, tau = onp.allan_var(g['x'], float(g['fs']))
+    assert_close(tau, g['tau'], 1e-15, what='tau')
+    assert_close(avar, g['avar'], 1e-12, 0.0, what='avar')
+    assert len(tau) == 38
+    avar, tau = onp.allan_var(g['x2'], float(g['fs2']))
+    assert_close(avar, g['avar2'], 1e-12, 0.0, what='avar2')
+    assert_close(tau, g['tau2'], 1e-15, what='tau2')
+    a, t = onp.allan_var(g['x3'], 100.0)
+    assert len(a) == 0 and len(t) == 0
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_psd_matches_reference(tag):
+    g = load_golden('psd.npz')
+    ok, x = onp.time_series_from_psd(g['sxx_' + tag], g['freq_' + tag], float(g['fs_' + tag]),
+                                     int(g['n_' + tag]), g['z_' + tag])
+    assert ok
+    assert_close(x, g['x_' + tag], 1e-12, what='psd series')
+
+
+def test_golden_survey_values():
+    """The end values quoted in SURVEY 8(c) are the ones in the fixtures."""
+    g = load_golden('logged_bosch.npz')
+    assert_close(g['att'][-1], [-0.04581388717726487, -0.01158326991382768, -0.0113185715399397],
+                 1e-14)
+    g = load_golden('seeded_90deg_rf1.npz')
+    assert_close(g['att'][0, -1], [7.8534050869474481e-01, -2.0678960287434905e-04,
+                                   9.5098666116010674e-05], 1e-13)
+    assert_close(g['pos'][0, -1], [-2707376.9803619734, 4688713.859123157, 3360102.3087808033],
+                 1e-15)
