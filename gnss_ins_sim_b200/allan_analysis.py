@@ -1,0 +1,49 @@
+"""Allan plugin -- device-backed mirror of demo_algorithms/allan_analysis.py:15-61
+(input ['fs','accel','gyro'], output ['algo_time','ad_accel','ad_gyro']); the variance
+itself is csrc/allan_kernel.cuh (K4, allan.allan_var allan.py:18-59)."""
+import numpy as np
+import torch
+
+from . import engine
+
+
+class Allan(object):
+    '''
+    Allan deviation of the three accelerometer and three gyroscope channels.
+    '''
+
+    def __init__(self):
+        self.input = ['fs', 'accel', 'gyro']
+        self.output = ['algo_time', 'ad_accel', 'ad_gyro']
+        self.batch = True
+        self.results = None
+
+    def run(self, set_of_input):
+        '''
+        set_of_input = [fs, accel (n,3), gyro (n,3)]
+        '''
+        fs = set_of_input[0]
+        tau, ad_a, ad_g = self.run_batch(fs, np.asarray(set_of_input[1])[None],
+                                         np.asarray(set_of_input[2])[None])
+        self.results = [tau, ad_a[0], ad_g[0]]
+
+    def run_batch(self, fs, accel, gyro, to_host=True):
+        '''
+        accel, gyro: [R, n, 3].  Returns tau [ntau], ad_accel [R, ntau, 3], ad_gyro [R, ntau, 3]
+        (Allan DEVIATION = sqrt(avar), allan_analysis.py:47-49).
+        '''
+        a = engine.to_device(accel)
+        g = engine.to_device(gyro)
+        R, n, _ = a.shape
+        x = torch.stack([a, g])                   # [2, R, n, 3]
+        avar, tau = engine.allan(fs, x, n, 2 * R * 3, inner=3, outer_stride=3 * n, sample_stride=3)
+        ad = torch.sqrt(avar).reshape(2, R, 3, -1).permute(0, 1, 3, 2).contiguous()
+        if to_host:
+            return tau.cpu().numpy(), ad[0].cpu().numpy(), ad[1].cpu().numpy()
+        return tau, ad[0], ad[1]
+
+    def get_results(self):
+        return self.results
+
+    def reset(self):
+        pass

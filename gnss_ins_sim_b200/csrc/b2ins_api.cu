@@ -1,0 +1,581 @@
+// b2ins C ABI (include/b2ins.h): argument checking, host-side pre-digestion of the error
+// models, kernel dispatch, and the *_host convenience wrappers.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../../include/b2ins.h"
+#include "allan_kernel.cuh"
+#include "mc_kernel.cuh"
+#include "noise_kernel.cuh"
+#include "stats_kernel.cuh"
+
+using namespace b2ins;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_CHECK(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(B2INS_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                              \
+  } while (0)
+
+#define ARG_CHECK(cond, ...) \
+  do {                       \
+    if (!(cond)) return fail(B2INS_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// bias_drift coefficients exactly as written at pathgen.py:583-586 (a: first-order
+// approximation, b: exact exponential) and the white-noise scale rw/sqrt(dt) (:496-498).
+int digest_triad(const b2ins_sensor_err* e, const b2ins_vib* v, double fs, TriadNoise* out) {
+  const double dt = 1.0 / fs;
+  for (int c = 0; c < 3; ++c) {
+    out->b[c] = e->b[c];
+    if (std::isinf(e->b_corr[c])) {
+      out->gm_a[c] = 0.0;
+      out->gm_b[c] = 0.0;
+      out->wd[c] = e->b_drift[c];
+    } else {
+      out->gm_a[c] = 1 - 1 / fs / e->b_corr[c];
+      out->gm_b[c] = e->b_drift[c] * std::sqrt(1.0 - std::exp(-2 / (fs * e->b_corr[c])));
+      out->wd[c] = 0.0;
+    }
+    out->w[c] = e->rw[c] / std::sqrt(dt);
+  }
+  out->vib_type = B2INS_VIB_NONE;
+  out->series_len = 0;
+  out->series = nullptr;
+  out->vib_w = 0.0;
+  for (int c = 0; c < 3; ++c) out->vib_amp[c] = 0.0;
+  if (v && v->type != B2INS_VIB_NONE) {
+    ARG_CHECK(v->type >= 1 && v->type <= 3, "vib type %d is not one of B2INS_VIB_*", v->type);
+    out->vib_type = v->type;
+    for (int c = 0; c < 3; ++c) out->vib_amp[c] = v->amp[c];
+    out->vib_w = 2.0 * M_PI * v->freq * dt;  // np.sin(2.0*math.pi*freq*dt*k), pathgen.py:491
+    if (v->type == B2INS_VIB_SERIES) {
+      ARG_CHECK(v->series && v->series_len > 0, "VIB_SERIES needs series and series_len > 0");
+      out->series = v->series;
+      out->series_len = v->series_len;
+    }
+  }
+  return B2INS_OK;
+}
+
+void layout_strides(int layout, int64_t runs, int64_t n, int64_t* sr, int64_t* st, int64_t* sc) {
+  if (layout == B2INS_LAYOUT_RUN_MAJOR) {
+    *sr = n * 3;
+    *st = 3;
+    *sc = 1;
+  } else {
+    *sr = 1;
+    *st = 3 * runs;
+    *sc = runs;
+  }
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      cached = 148;
+  }
+  return cached;
+}
+
+// Lanes per run: the mechanization is serial in time, so the only parallelism is across
+// runs (and across the G samples of a block in phase A).  Instruction cost per run-step is
+// roughly (A + G*B)/32 warp-instructions, so G = 1 is the throughput optimum once there
+// are enough runs to give every SM sub-partition several warps; with fewer runs a wider
+// group buys latency (more warps in flight, phase A amortised over G samples).
+int auto_lanes(int64_t runs) {
+  const int64_t target_warps = static_cast<int64_t>(sm_count()) * 4 * 4;  // 4 warps / SMSP
+  int g = 1;
+  while (g < 32 && runs * g < target_warps * 32) g <<= 1;
+  return g;
+}
+
+template <int G, int RF>
+void launch_mc_grf(const McParams& p, bool fed, bool proc, cudaStream_t s) {
+  const int64_t runs_per_cta = static_cast<int64_t>(kWarps) * (32 / G);
+  const unsigned grid = static_cast<unsigned>((p.runs + runs_per_cta - 1) / runs_per_cta);
+  if (fed) {
+    if (proc)
+      mc_kernel<G, RF, true, true><<<grid, kThreads, 0, s>>>(p);
+    else
+      mc_kernel<G, RF, true, false><<<grid, kThreads, 0, s>>>(p);
+  } else {
+    if (proc)
+      mc_kernel<G, RF, false, true><<<grid, kThreads, 0, s>>>(p);
+    else
+      mc_kernel<G, RF, false, false><<<grid, kThreads, 0, s>>>(p);
+  }
+}
+
+template <int G>
+void launch_mc_g(const McParams& p, int rf, bool fed, bool proc, cudaStream_t s) {
+  if (rf == 1)
+    launch_mc_grf<G, 1>(p, fed, proc, s);
+  else
+    launch_mc_grf<G, 0>(p, fed, proc, s);
+}
+
+int launch_mc(const McParams& p, int lanes, int rf, bool fed, bool proc, cudaStream_t s) {
+  switch (lanes) {
+    case 1: launch_mc_g<1>(p, rf, fed, proc, s); break;
+    case 2: launch_mc_g<2>(p, rf, fed, proc, s); break;
+    case 4: launch_mc_g<4>(p, rf, fed, proc, s); break;
+    case 8: launch_mc_g<8>(p, rf, fed, proc, s); break;
+    case 16: launch_mc_g<16>(p, rf, fed, proc, s); break;
+    case 32: launch_mc_g<32>(p, rf, fed, proc, s); break;
+    default: return fail(B2INS_ERR_ARG, "lanes_per_run must be 0,1,2,4,8,16 or 32, got %d", lanes);
+  }
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  double* d() const { return static_cast<double*>(p); }
+};
+
+struct Stream {
+  cudaStream_t s = nullptr;
+  ~Stream() {
+    if (s) cudaStreamDestroy(s);
+  }
+  cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int b2ins_version(void) { return B2INS_VERSION; }
+
+const char* b2ins_last_error(void) { return g_err; }
+
+int b2ins_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// allan.py:29-44
+int b2ins_allan_num_tau(int64_t n, double fs, int64_t* m, int m_cap) {
+  const double ts = 1.0 / fs;
+  const int64_t max_bin = static_cast<int64_t>(std::floor(n / 9.0));
+  if (max_bin * ts < 1) return 0;
+  const int nextpow10 = static_cast<int>(std::ceil(std::log10(static_cast<double>(max_bin))));
+  int count = 0;
+  double scale = 0.1;
+  for (int i = 0; i < nextpow10; ++i) {
+    scale *= 10;
+    for (int j = 1; j < 10; ++j) {
+      const int64_t tmp = static_cast<int64_t>(j * scale);
+      if (tmp <= max_bin) {
+        if (m && count < m_cap) m[count] = tmp;
+        ++count;
+      } else {
+        break;
+      }
+    }
+  }
+  return count;
+}
+
+// ---------------------------------------------------------------- K2 --------
+int b2ins_free_integration_f64(int ref_frame, double fs, int64_t runs, int64_t n,
+                               const double* gyro, const double* accel, int layout,
+                               const double* ini, int ini_sets, int ini_rows, int64_t run_offset,
+                               int earth_rot, double* att, double* pos, double* vel,
+                               int lanes_per_run, void* stream) {
+  ARG_CHECK(ref_frame == 0 || ref_frame == 1, "ref_frame must be 0 or 1, got %d", ref_frame);
+  ARG_CHECK(fs > 0.0, "fs must be positive");
+  ARG_CHECK(runs >= 0 && n >= 0, "runs and n must be non-negative");
+  ARG_CHECK(layout == 0 || layout == 1, "layout must be B2INS_LAYOUT_*");
+  ARG_CHECK(ini_sets >= 1 && (ini_rows == 9 || ini_rows == 10), "ini must be [sets>=1][9|10]");
+  if (runs == 0 || n == 0) return B2INS_OK;
+  ARG_CHECK(gyro && accel && ini && att && pos && vel, "null buffer");
+  ARG_CHECK(n < (int64_t(1) << 32), "n must be < 2^32");
+  McParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = n;
+  p.runs = runs;
+  p.run_offset = run_offset;
+  p.ini_offset = run_offset;
+  p.dt = 1.0 / fs;
+  p.earth_rot = earth_rot;
+  p.ini = ini;
+  p.ini_sets = ini_sets;
+  p.ini_rows = ini_rows;
+  p.fed_gyro = gyro;
+  p.fed_accel = accel;
+  layout_strides(layout, runs, n, &p.sr, &p.st, &p.sc);
+  p.out_att = att;
+  p.out_pos = pos;
+  p.out_vel = vel;
+  p.osr = p.sr;
+  p.ost = p.st;
+  p.osc = p.sc;
+  p.dump_runs = runs;
+  p.stats_start = -1;
+  int lanes = lanes_per_run;
+  if (lanes == 0) {
+    lanes = auto_lanes(runs);
+    // run-major rows are 24-byte strided per lane when G = 1; a wider group reads whole
+    // contiguous stretches of one run
+    if (layout == B2INS_LAYOUT_RUN_MAJOR && lanes < 8) lanes = 8;
+  }
+  return launch_mc(p, lanes, ref_frame, true, false, static_cast<cudaStream_t>(stream));
+}
+
+int b2ins_free_integration_f64_host(int ref_frame, double fs, int64_t runs, int64_t n,
+                                    const double* gyro, const double* accel, int layout,
+                                    const double* ini, int ini_sets, int ini_rows,
+                                    int64_t run_offset, int earth_rot, double* att, double* pos,
+                                    double* vel, int lanes_per_run) {
+  ARG_CHECK(runs >= 0 && n >= 0, "runs and n must be non-negative");
+  if (runs == 0 || n == 0) return B2INS_OK;
+  ARG_CHECK(gyro && accel && ini && att && pos && vel, "null buffer");
+  ARG_CHECK(ini_sets >= 1 && (ini_rows == 9 || ini_rows == 10), "ini must be [sets>=1][9|10]");
+  const size_t bytes = static_cast<size_t>(runs) * n * 3 * sizeof(double);
+  const size_t ini_bytes = static_cast<size_t>(ini_sets) * ini_rows * sizeof(double);
+  DevBuf dg, da, di, oa, op, ov;
+  Stream st;
+  CU_CHECK(st.create());
+  CU_CHECK(dg.alloc(bytes));
+  CU_CHECK(da.alloc(bytes));
+  CU_CHECK(di.alloc(ini_bytes));
+  CU_CHECK(oa.alloc(bytes));
+  CU_CHECK(op.alloc(bytes));
+  CU_CHECK(ov.alloc(bytes));
+  CU_CHECK(cudaMemcpyAsync(dg.p, gyro, bytes, cudaMemcpyHostToDevice, st.s));
+  CU_CHECK(cudaMemcpyAsync(da.p, accel, bytes, cudaMemcpyHostToDevice, st.s));
+  CU_CHECK(cudaMemcpyAsync(di.p, ini, ini_bytes, cudaMemcpyHostToDevice, st.s));
+  const int rc = b2ins_free_integration_f64(ref_frame, fs, runs, n, dg.d(), da.d(), layout, di.d(),
+                                            ini_sets, ini_rows, run_offset, earth_rot, oa.d(),
+                                            op.d(), ov.d(), lanes_per_run, st.s);
+  if (rc != B2INS_OK) return rc;
+  CU_CHECK(cudaMemcpyAsync(att, oa.p, bytes, cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaMemcpyAsync(pos, op.p, bytes, cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaMemcpyAsync(vel, ov.p, bytes, cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaStreamSynchronize(st.s));
+  return B2INS_OK;
+}
+
+// ---------------------------------------------------------------- K1 --------
+int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gyro,
+                        const double* ref_accel, const b2ins_sensor_err* gyro_err,
+                        const b2ins_sensor_err* accel_err, const b2ins_vib* vib_gyro,
+                        const b2ins_vib* vib_accel, uint64_t seed, int64_t run_offset, int layout,
+                        double* gyro, double* accel, double* z_dump, void* stream) {
+  ARG_CHECK(fs > 0.0, "fs must be positive");
+  ARG_CHECK(runs >= 0 && n >= 0, "runs and n must be non-negative");
+  ARG_CHECK(layout == 0 || layout == 1, "layout must be B2INS_LAYOUT_*");
+  if (runs == 0 || n == 0) return B2INS_OK;
+  ARG_CHECK(ref_gyro && ref_accel && gyro_err && accel_err && gyro && accel, "null buffer");
+  ARG_CHECK(n < (int64_t(1) << 32), "n must be < 2^32");
+  NoiseParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = n;
+  p.runs = runs;
+  p.run_offset = run_offset;
+  p.dt = 1.0 / fs;
+  p.k0 = static_cast<uint32_t>(seed);
+  p.k1 = static_cast<uint32_t>(seed >> 32);
+  int rc = digest_triad(gyro_err, vib_gyro, fs, &p.gyro);
+  if (rc != B2INS_OK) return rc;
+  rc = digest_triad(accel_err, vib_accel, fs, &p.accel);
+  if (rc != B2INS_OK) return rc;
+  p.ref_gyro = ref_gyro;
+  p.ref_accel = ref_accel;
+  p.out_gyro = gyro;
+  p.out_accel = accel;
+  layout_strides(layout, runs, n, &p.osr, &p.ost, &p.osc);
+  p.z_dump = z_dump;
+  imu_noise_kernel<<<static_cast<unsigned>(runs), kNoiseThreads, 0,
+                     static_cast<cudaStream_t>(stream)>>>(p);
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+int b2ins_imu_noise_f64_host(double fs, int64_t runs, int64_t n, const double* ref_gyro,
+                             const double* ref_accel, const b2ins_sensor_err* gyro_err,
+                             const b2ins_sensor_err* accel_err, const b2ins_vib* vib_gyro,
+                             const b2ins_vib* vib_accel, uint64_t seed, int64_t run_offset,
+                             int layout, double* gyro, double* accel, double* z_dump) {
+  ARG_CHECK(runs >= 0 && n >= 0, "runs and n must be non-negative");
+  if (runs == 0 || n == 0) return B2INS_OK;
+  ARG_CHECK(ref_gyro && ref_accel && gyro && accel, "null buffer");
+  ARG_CHECK(!(vib_gyro && vib_gyro->type == B2INS_VIB_SERIES) &&
+                !(vib_accel && vib_accel->type == B2INS_VIB_SERIES),
+            "VIB_SERIES takes a device pointer: use the device entry point");
+  const size_t ref_bytes = static_cast<size_t>(n) * 3 * sizeof(double);
+  const size_t bytes = static_cast<size_t>(runs) * ref_bytes;
+  DevBuf rg, ra, og, oa, zd;
+  Stream st;
+  CU_CHECK(st.create());
+  CU_CHECK(rg.alloc(ref_bytes));
+  CU_CHECK(ra.alloc(ref_bytes));
+  CU_CHECK(og.alloc(bytes));
+  CU_CHECK(oa.alloc(bytes));
+  if (z_dump) CU_CHECK(zd.alloc(bytes * 4));
+  CU_CHECK(cudaMemcpyAsync(rg.p, ref_gyro, ref_bytes, cudaMemcpyHostToDevice, st.s));
+  CU_CHECK(cudaMemcpyAsync(ra.p, ref_accel, ref_bytes, cudaMemcpyHostToDevice, st.s));
+  const int rc = b2ins_imu_noise_f64(fs, runs, n, rg.d(), ra.d(), gyro_err, accel_err, vib_gyro,
+                                     vib_accel, seed, run_offset, layout, og.d(), oa.d(),
+                                     z_dump ? zd.d() : nullptr, st.s);
+  if (rc != B2INS_OK) return rc;
+  CU_CHECK(cudaMemcpyAsync(gyro, og.p, bytes, cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaMemcpyAsync(accel, oa.p, bytes, cudaMemcpyDeviceToHost, st.s));
+  if (z_dump) CU_CHECK(cudaMemcpyAsync(z_dump, zd.p, bytes * 4, cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaStreamSynchronize(st.s));
+  return B2INS_OK;
+}
+
+// ---------------------------------------------------------------- K12 -------
+int b2ins_mc_free_integration_f64(const b2ins_mc_config* cfg, const double* ref_gyro,
+                                  const double* ref_accel, const double* ref_nav,
+                                  const double* ini, double* end_err, double* end_state,
+                                  double* proc_stats, double* dump_att, double* dump_pos,
+                                  double* dump_vel, double* dump_gyro, double* dump_accel,
+                                  void* stream) {
+  ARG_CHECK(cfg, "cfg is null");
+  ARG_CHECK(cfg->ref_frame == 0 || cfg->ref_frame == 1, "ref_frame must be 0 or 1");
+  ARG_CHECK(cfg->fs > 0.0, "fs must be positive");
+  ARG_CHECK(cfg->runs >= 0 && cfg->n >= 0, "runs and n must be non-negative");
+  ARG_CHECK(cfg->ini_sets >= 1 && (cfg->ini_rows == 9 || cfg->ini_rows == 10),
+            "ini must be [sets>=1][9|10]");
+  if (cfg->runs == 0 || cfg->n == 0) return B2INS_OK;
+  ARG_CHECK(ref_gyro && ref_accel && ini, "null input buffer");
+  ARG_CHECK(aligned16(ref_gyro) && aligned16(ref_accel) && aligned16(ref_nav),
+            "ref_gyro / ref_accel / ref_nav must be 16-byte aligned (bulk async copies)");
+  ARG_CHECK(cfg->n < (int64_t(1) << 32), "n must be < 2^32");
+  ARG_CHECK(!(end_err || cfg->stats_start >= 0) || ref_nav, "ref_nav is needed for errors");
+  ARG_CHECK(cfg->stats_start < 0 || proc_stats, "stats_start >= 0 needs proc_stats");
+  ARG_CHECK(cfg->dump_runs >= 0 && cfg->dump_runs <= cfg->runs, "dump_runs out of range");
+  ARG_CHECK((!dump_att && !dump_pos && !dump_vel) || (dump_att && dump_pos && dump_vel),
+            "dump_att/pos/vel must be given together");
+  ARG_CHECK((!dump_gyro) == (!dump_accel), "dump_gyro/accel must be given together");
+  McParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = cfg->n;
+  p.runs = cfg->runs;
+  p.run_offset = cfg->run_offset;
+  p.ini_offset = cfg->ini_offset;
+  p.dt = 1.0 / cfg->fs;
+  p.earth_rot = cfg->earth_rot;
+  p.k0 = static_cast<uint32_t>(cfg->seed);
+  p.k1 = static_cast<uint32_t>(cfg->seed >> 32);
+  int rc = digest_triad(&cfg->gyro_err, &cfg->vib_gyro, cfg->fs, &p.gyro);
+  if (rc != B2INS_OK) return rc;
+  rc = digest_triad(&cfg->accel_err, &cfg->vib_accel, cfg->fs, &p.accel);
+  if (rc != B2INS_OK) return rc;
+  p.ref_gyro = ref_gyro;
+  p.ref_accel = ref_accel;
+  p.ref_nav = ref_nav;
+  p.ini = ini;
+  p.ini_sets = cfg->ini_sets;
+  p.ini_rows = cfg->ini_rows;
+  p.out_att = dump_att;
+  p.out_pos = dump_pos;
+  p.out_vel = dump_vel;
+  p.out_gyro = dump_gyro;
+  p.out_accel = dump_accel;
+  layout_strides(B2INS_LAYOUT_RUN_MAJOR, cfg->dump_runs, cfg->n, &p.osr, &p.ost, &p.osc);
+  p.dump_runs = (dump_att || dump_gyro) ? cfg->dump_runs : 0;
+  p.end_err = end_err;
+  p.end_state = end_state;
+  p.proc_stats = proc_stats;
+  p.stats_start = cfg->stats_start;
+  const int lanes = cfg->lanes_per_run ? cfg->lanes_per_run : auto_lanes(cfg->runs);
+  return launch_mc(p, lanes, cfg->ref_frame, false, cfg->stats_start >= 0,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int b2ins_mc_free_integration_f64_host(const b2ins_mc_config* cfg, const double* ref_gyro,
+                                       const double* ref_accel, const double* ref_nav,
+                                       const double* ini, double* end_err, double* stats) {
+  ARG_CHECK(cfg, "cfg is null");
+  ARG_CHECK(cfg->runs > 0 && cfg->n > 0, "runs and n must be positive");
+  ARG_CHECK(ref_gyro && ref_accel && ref_nav && ini && stats, "null buffer");
+  ARG_CHECK(cfg->vib_gyro.type != B2INS_VIB_SERIES && cfg->vib_accel.type != B2INS_VIB_SERIES,
+            "VIB_SERIES takes a device pointer: use the device entry point");
+  ARG_CHECK(cfg->ini_sets >= 1 && (cfg->ini_rows == 9 || cfg->ini_rows == 10),
+            "ini must be [sets>=1][9|10]");
+  const size_t ref_bytes = static_cast<size_t>(cfg->n) * 3 * sizeof(double);
+  const size_t ini_bytes = static_cast<size_t>(cfg->ini_sets) * cfg->ini_rows * sizeof(double);
+  const size_t err_bytes = static_cast<size_t>(cfg->runs) * 9 * sizeof(double);
+  DevBuf rg, ra, rn, di, de, ds, ws;
+  Stream st;
+  CU_CHECK(st.create());
+  CU_CHECK(rg.alloc(ref_bytes));
+  CU_CHECK(ra.alloc(ref_bytes));
+  CU_CHECK(rn.alloc(ref_bytes * 3));
+  CU_CHECK(di.alloc(ini_bytes));
+  CU_CHECK(de.alloc(err_bytes));
+  CU_CHECK(ds.alloc(27 * sizeof(double)));
+  CU_CHECK(ws.alloc(static_cast<size_t>(b2ins_error_stats_workspace_bytes(9))));
+  CU_CHECK(cudaMemcpyAsync(rg.p, ref_gyro, ref_bytes, cudaMemcpyHostToDevice, st.s));
+  CU_CHECK(cudaMemcpyAsync(ra.p, ref_accel, ref_bytes, cudaMemcpyHostToDevice, st.s));
+  CU_CHECK(cudaMemcpyAsync(rn.p, ref_nav, ref_bytes * 3, cudaMemcpyHostToDevice, st.s));
+  CU_CHECK(cudaMemcpyAsync(di.p, ini, ini_bytes, cudaMemcpyHostToDevice, st.s));
+  b2ins_mc_config c = *cfg;
+  c.stats_start = -1;
+  c.dump_runs = 0;
+  int rc = b2ins_mc_free_integration_f64(&c, rg.d(), ra.d(), rn.d(), di.d(), de.d(), nullptr,
+                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                         st.s);
+  if (rc != B2INS_OK) return rc;
+  rc = b2ins_error_stats_f64(cfg->runs, 9, de.d(), ds.d(), ws.d(), st.s);
+  if (rc != B2INS_OK) return rc;
+  if (end_err) CU_CHECK(cudaMemcpyAsync(end_err, de.p, err_bytes, cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaMemcpyAsync(stats, ds.p, 27 * sizeof(double), cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaStreamSynchronize(st.s));
+  return B2INS_OK;
+}
+
+// ---------------------------------------------------------------- K3 --------
+int64_t b2ins_error_stats_workspace_bytes(int ncomp) {
+  if (ncomp < 1) return 0;
+  // per-block partials + partial[2nc] + mean... : [kStatBlocks][2][nc] + 4*nc
+  return static_cast<int64_t>(sizeof(double)) * (static_cast<int64_t>(kStatBlocks) * 2 + 4) * ncomp;
+}
+
+static int stage1_grid(int64_t runs, int ncomp, int threads) {
+  const int64_t total = runs * ncomp;
+  int64_t g = (total + threads - 1) / threads;
+  if (g > kStatBlocks) g = kStatBlocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int b2ins_error_partial_f64(int64_t runs, int ncomp, const double* err, double* partial,
+                            void* workspace, void* stream) {
+  ARG_CHECK(runs > 0 && ncomp >= 1 && ncomp <= kStatMaxComp, "bad runs/ncomp");
+  ARG_CHECK(err && partial && workspace, "null buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = stat_threads(ncomp);
+  const int grid = stage1_grid(runs, ncomp, threads);
+  double* ws = static_cast<double*>(workspace);
+  err_stage1_kernel<0><<<grid, threads, 2 * threads * sizeof(double), s>>>(runs, ncomp, err,
+                                                                           nullptr, ws);
+  err_stage2_kernel<0><<<1, 32, 0, s>>>(grid, ncomp, ws, partial);
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+int b2ins_error_partial2_f64(int64_t runs, int ncomp, const double* err, const double* mean,
+                             double* partial2, void* workspace, void* stream) {
+  ARG_CHECK(runs > 0 && ncomp >= 1 && ncomp <= kStatMaxComp, "bad runs/ncomp");
+  ARG_CHECK(err && mean && partial2 && workspace, "null buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = stat_threads(ncomp);
+  const int grid = stage1_grid(runs, ncomp, threads);
+  double* ws = static_cast<double*>(workspace);
+  err_stage1_kernel<1><<<grid, threads, 2 * threads * sizeof(double), s>>>(runs, ncomp, err, mean,
+                                                                           ws);
+  err_stage2_kernel<1><<<1, 32, 0, s>>>(grid, ncomp, ws, partial2);
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+int b2ins_error_stats_f64(int64_t runs, int ncomp, const double* err, double* stats,
+                          void* workspace, void* stream) {
+  ARG_CHECK(runs > 0 && ncomp >= 1 && ncomp <= kStatMaxComp, "bad runs/ncomp");
+  ARG_CHECK(err && stats && workspace, "null buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* ws = static_cast<double*>(workspace);
+  double* partial = ws + static_cast<int64_t>(kStatBlocks) * 2 * ncomp;  // [2nc]
+  double* partial2 = partial + 2 * ncomp;                                // [nc]
+  int rc = b2ins_error_partial_f64(runs, ncomp, err, partial, workspace, stream);
+  if (rc != B2INS_OK) return rc;
+  stats_mean_kernel<<<1, 32, 0, s>>>(runs, ncomp, partial, stats);
+  rc = b2ins_error_partial2_f64(runs, ncomp, err, stats + ncomp, partial2, workspace, stream);
+  if (rc != B2INS_OK) return rc;
+  stats_std_kernel<<<1, 32, 0, s>>>(runs, ncomp, partial2, stats);
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+// ---------------------------------------------------------------- K4 --------
+int64_t b2ins_allan_workspace_bytes(int64_t n, int64_t nseries) {
+  return allan_workspace_bytes(n, nseries);
+}
+
+int b2ins_allan_f64(double fs, int64_t n, int64_t nseries, const double* x, int64_t inner,
+                    int64_t outer_stride, int64_t sample_stride, double* avar, double* tau,
+                    void* workspace, void* stream) {
+  ARG_CHECK(fs > 0.0 && n >= 0 && nseries >= 0, "bad fs/n/nseries");
+  ARG_CHECK(inner >= 1 && sample_stride >= 1, "bad strides");
+  int64_t mult[128];
+  const int ntau = b2ins_allan_num_tau(n, fs, mult, 128);
+  if (ntau == 0 || nseries == 0) return B2INS_OK;
+  ARG_CHECK(ntau <= 128, "too many tau");
+  ARG_CHECK(x && avar && tau && workspace, "null buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rc = allan_launch(fs, n, nseries, x, inner, outer_stride, sample_stride, mult, ntau,
+                              avar, tau, workspace, s);
+  if (rc != 0) return fail(B2INS_ERR_CUDA, "allan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+int b2ins_allan_f64_host(double fs, int64_t n, int64_t nseries, const double* x, int64_t inner,
+                         int64_t outer_stride, int64_t sample_stride, double* avar, double* tau) {
+  ARG_CHECK(fs > 0.0 && n >= 0 && nseries >= 0, "bad fs/n/nseries");
+  ARG_CHECK(inner >= 1 && sample_stride >= 1, "bad strides");
+  const int ntau = b2ins_allan_num_tau(n, fs, nullptr, 0);
+  if (ntau == 0 || nseries == 0) return B2INS_OK;
+  ARG_CHECK(x && avar && tau, "null buffer");
+  // extent of x touched
+  const int64_t outer = (nseries + inner - 1) / inner;
+  const int64_t elems = (outer - 1) * outer_stride + (inner - 1) + (n - 1) * sample_stride + 1;
+  DevBuf dx, dav, dtau, ws;
+  Stream st;
+  CU_CHECK(st.create());
+  CU_CHECK(dx.alloc(static_cast<size_t>(elems) * sizeof(double)));
+  CU_CHECK(dav.alloc(static_cast<size_t>(nseries) * ntau * sizeof(double)));
+  CU_CHECK(dtau.alloc(static_cast<size_t>(ntau) * sizeof(double)));
+  CU_CHECK(ws.alloc(static_cast<size_t>(allan_workspace_bytes(n, nseries))));
+  CU_CHECK(cudaMemcpyAsync(dx.p, x, static_cast<size_t>(elems) * sizeof(double),
+                           cudaMemcpyHostToDevice, st.s));
+  const int rc = b2ins_allan_f64(fs, n, nseries, dx.d(), inner, outer_stride, sample_stride,
+                                 dav.d(), dtau.d(), ws.p, st.s);
+  if (rc != B2INS_OK) return rc;
+  CU_CHECK(cudaMemcpyAsync(avar, dav.p, static_cast<size_t>(nseries) * ntau * sizeof(double),
+                           cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaMemcpyAsync(tau, dtau.p, static_cast<size_t>(ntau) * sizeof(double),
+                           cudaMemcpyDeviceToHost, st.s));
+  CU_CHECK(cudaStreamSynchronize(st.s));
+  return B2INS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// K2 / K12: the Monte-Carlo strapdown kernel.
+//
+// One LANE GROUP of G lanes (G = 1,2,4,...,32) owns one Monte-Carlo run; G = 32 is
+// "one warp owns one run".  Per block of G consecutive samples:
+//   phase A (time-parallel): lane j prepares sample base+j -- Philox4x32-10 + Box-Muller
+//           normals, white noise, constant bias, vibration added to the true IMU sample
+//           (read from the TMA-staged shared-memory tile), or the fed gyro/accel sample.
+//   phase B (serial in time): for k = 0..G-1 every lane of the group pulls sample base+k
+//           from lane k by warp shuffle, advances the Gauss-Markov bias and the 9-DoF
+//           strapdown state (registers, replicated across the group) by one step.
+// The shared true trajectory (ref gyro/accel [n][3], optionally ref nav [n][9]) is staged
+// through shared memory in tiles of kTile samples by 1-D bulk async copies (TMA) completing
+// on mbarriers, kStages deep, one pipeline per CTA shared by all its runs.
+#pragma once
+#include "mech.cuh"
+
+namespace b2ins {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTile = 128;   // samples per shared-memory tile (multiple of 32)
+constexpr int kStages = 3;
+
+// error model of one triad, pre-digested on the host (bias_drift: pathgen.py:583-586)
+struct TriadNoise {
+  double b[3];        // constant bias
+  double gm_a[3];     // 1 - dt/tau            (0 if the drift is white)
+  double gm_b[3];     // drift*sqrt(1-exp(-2dt/tau))  (0 if the drift is white)
+  double wd[3];       // drift sigma if the drift is white (corr = inf), else 0
+  double w[3];        // rw / sqrt(dt)
+  int vib_type;
+  int series_len;
+  double vib_amp[3];
+  double vib_w;       // ((2 pi) f) dt
+  const double* series;  // [runs][3][series_len]
+};
+
+struct McParams {
+  int64_t n, runs, run_offset, ini_offset;
+  double dt;
+  int earth_rot;
+  uint32_t k0, k1;
+  TriadNoise gyro, accel;
+  const double* ref_gyro;   // [n][3]
+  const double* ref_accel;  // [n][3]
+  const double* ref_nav;    // [n][9] att, pos, vel
+  const double* ini;        // [ini_sets][ini_rows]
+  int ini_sets, ini_rows;
+  // fed measurements (K2) -- element (r,t,c) at r*sr + t*st + c*sc
+  const double* fed_gyro;
+  const double* fed_accel;
+  int64_t sr, st, sc;
+  // histories for runs [0, dump_runs): same stride convention
+  double* out_att;
+  double* out_pos;
+  double* out_vel;
+  double* out_gyro;
+  double* out_accel;
+  int64_t osr, ost, osc;
+  int64_t dump_runs;
+  // per-run results
+  double* end_err;     // [runs][9]
+  double* end_state;   // [runs][9]
+  double* proc_stats;  // [runs][3][9]
+  int64_t stats_start;
+};
+
+struct Sample {
+  double g[3], a[3];    // measurement without the GM drift
+  double zg[3], za[3];  // GM drive normals
+};
+
+struct TileSmem {
+  alignas(128) double gyro[kStages][kTile * 3];
+  alignas(128) double accel[kStages][kTile * 3];
+  alignas(128) double nav[kStages][kTile * 9];
+  alignas(8) uint64_t full[kStages];
+  alignas(8) uint64_t empty[kStages];
+};
+
+// Issue the copies of one tile: the 16-byte-multiple part by bulk async copy (TMA)
+// completing on full[s]; an odd sample count leaves one 8-byte tail copied by hand.
+template <bool FED, bool PROC>
+__device__ __forceinline__ void issue_tile(TileSmem& sm, const McParams& p, int64_t tile, int s) {
+  const int64_t t0 = tile * kTile;
+  const uint32_t cnt = static_cast<uint32_t>(min64(kTile, p.n - t0));
+  uint32_t tx = 0;
+  if (!FED) tx += 2u * ((cnt * 24u) & ~15u);
+  if (PROC) tx += (cnt * 72u) & ~15u;
+  // the hand-copied tails are ordered before the arrive (release) below
+  if (!FED) {
+    if ((cnt * 24u) & 8u) {
+      const uint32_t o = ((cnt * 24u) & ~15u) / 8;
+      sm.gyro[s][o] = p.ref_gyro[t0 * 3 + o];
+      sm.accel[s][o] = p.ref_accel[t0 * 3 + o];
+    }
+  }
+  if (PROC) {
+    if ((cnt * 72u) & 8u) {
+      const uint32_t o = ((cnt * 72u) & ~15u) / 8;
+      sm.nav[s][o] = p.ref_nav[t0 * 9 + o];
+    }
+  }
+  mbar_arrive_expect_tx(&sm.full[s], tx);
+  if (!FED) {
+    const uint32_t b = (cnt * 24u) & ~15u;
+    if (b) {
+      bulk_g2s(sm.gyro[s], p.ref_gyro + t0 * 3, b, &sm.full[s]);
+      bulk_g2s(sm.accel[s], p.ref_accel + t0 * 3, b, &sm.full[s]);
+    }
+  }
+  if (PROC) {
+    const uint32_t b = (cnt * 72u) & ~15u;
+    if (b) bulk_g2s(sm.nav[s], p.ref_nav + t0 * 9, b, &sm.full[s]);
+  }
+}
+
+// phase A for one triad in Monte-Carlo mode: (ref + b) + white + vib, and the GM normals
+__device__ __forceinline__ void noisy_triad(const TriadNoise& e, const double* ref3, uint32_t t,
+                                            uint32_t draw0, int sensor, uint32_t run_lo,
+                                            uint32_t run_hi, uint32_t k0, uint32_t k1,
+                                            int64_t run_local, const double* phase,
+                                            double* m, double* zgm) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const Normal2 z = normal_pair(t, draw0 + c, run_lo, run_hi, k0, k1);
+    zgm[c] = z.z0;
+    double v = (ref3[c] + e.b[c]) + e.w[c] * z.z1;
+    if (e.vib_type == 1) {
+      const Normal2 zv = normal_pair(t, kDrawVib + c, run_lo, run_hi, k0, k1);
+      v += e.vib_amp[c] * (sensor == 0 ? zv.z0 : zv.z1);
+    } else if (e.vib_type == 2) {
+      const double arg = e.vib_w * static_cast<double>(t) + (sensor == 0 ? 0.0 : phase[c]);
+      v += e.vib_amp[c] * sin(arg);
+    } else if (e.vib_type == 3) {
+      v += e.series[(run_local * 3 + c) * e.series_len + (t % static_cast<uint32_t>(e.series_len))];
+    }
+    m[c] = v;
+  }
+}
+
+template <int G, int RF, bool FED, bool PROC>
+__global__ void __launch_bounds__(kThreads)
+mc_kernel(const __grid_constant__ McParams p) {
+  __shared__ TileSmem sm;
+  constexpr int kRunsPerWarp = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int j = lane % G;
+  const int64_t run_raw =
+      (static_cast<int64_t>(blockIdx.x) * kWarps + warp) * kRunsPerWarp + lane / G;
+  const bool active = run_raw < p.runs;
+  const int64_t run = active ? run_raw : p.runs - 1;  // idle groups shadow the last run
+  const int64_t grun = p.run_offset + run;            // global run id
+  const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
+  const bool dump = active && run < p.dump_runs;
+  constexpr bool kStaged = !FED || PROC;
+
+  const int64_t num_tiles = (p.n + kTile - 1) / kTile;
+  if (kStaged) {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&sm.full[s], 1);
+        mbar_init(&sm.empty[s], kWarps);
+      }
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < kStages && s < num_tiles; ++s) issue_tile<FED, PROC>(sm, p, s, s);
+    }
+  }
+
+  // ---- sample 0 ----------------------------------------------------------
+  NavState st;
+  {
+    const int64_t irun = p.ini_offset + run;
+    const int64_t set = (irun < p.ini_sets) ? irun : 0;  // free_integration.py:85-87
+    nav_init<RF>(st, p.ini + set * p.ini_rows, p.ini_rows);
+  }
+  double dg[3] = {0.0, 0.0, 0.0}, da[3] = {0.0, 0.0, 0.0};  // GM drift, d[0] = 0
+  double phase[3] = {0.0, 0.0, 0.0};
+  if (!FED && p.gyro.vib_type == 2) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)  // np.random.rand(1)*2*pi, pathgen.py:553-555
+      phase[c] = (uniform01(0xFFFFFFFFu, kDrawPhase + c, run_lo, run_hi, p.k0, p.k1) * 2.0) * kPi;
+  }
+  if (dump && j == 0 && p.out_att) {
+    const int64_t o = run * p.osr;
+    p.out_att[o] = st.yaw;
+    p.out_att[o + p.osc] = st.pitch;
+    p.out_att[o + 2 * p.osc] = st.roll;
+    p.out_pos[o] = st.pos.x;
+    p.out_pos[o + p.osc] = st.pos.y;
+    p.out_pos[o + 2 * p.osc] = st.pos.z;
+    p.out_vel[o] = st.vel.x;
+    p.out_vel[o + p.osc] = st.vel.y;
+    p.out_vel[o + 2 * p.osc] = st.vel.z;
+  }
+  // process-error accumulators (shifted sums: K = first error sample)
+  double pe_max[9], pe_sum[9], pe_sq[9], pe_k[9];
+  int64_t pe_cnt = 0;
+  if (PROC) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) pe_max[c] = pe_sum[c] = pe_sq[c] = pe_k[c] = 0.0;
+  }
+
+  // ---- time loop ---------------------------------------------------------
+  for (int64_t tile = 0; tile < num_tiles; ++tile) {
+    const int s = static_cast<int>(tile % kStages);
+    const uint32_t parity = static_cast<uint32_t>((tile / kStages) & 1);
+    const int64_t t0 = tile * kTile;
+    const int cnt = static_cast<int>(min64(kTile, p.n - t0));
+    if (kStaged) mbar_wait(&sm.full[s], parity);
+
+    for (int base = 0; base < cnt; base += G) {
+      // ---------------- phase A: lane j prepares sample t0 + base + j --------------
+      Sample smp;
+      const int tj = base + j;
+      const int64_t t = t0 + tj;
+      if (tj < cnt) {
+        if (FED) {
+          const int64_t o = run * p.sr + t * p.st;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            smp.g[c] = p.fed_gyro[o + c * p.sc];
+            smp.a[c] = p.fed_accel[o + c * p.sc];
+            smp.zg[c] = smp.za[c] = 0.0;
+          }
+        } else {
+          noisy_triad(p.accel, &sm.accel[s][tj * 3], static_cast<uint32_t>(t), kDrawAccel, 0,
+                      run_lo, run_hi, p.k0, p.k1, run, phase, smp.a, smp.za);
+          noisy_triad(p.gyro, &sm.gyro[s][tj * 3], static_cast<uint32_t>(t), kDrawGyro, 1, run_lo,
+                      run_hi, p.k0, p.k1, run, phase, smp.g, smp.zg);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) smp.g[c] = smp.a[c] = smp.zg[c] = smp.za[c] = 0.0;
+      }
+
+      // ---------------- phase B: serial over the G samples of the block ------------
+      double keep[15];  // lane k keeps (gyro, accel) of sample base+k and the state after it
+#pragma unroll
+      for (int c = 0; c < 15; ++c) keep[c] = 0.0;
+      const int kmax = min(G, cnt - base);
+#pragma unroll 1
+      for (int k = 0; k < kmax; ++k) {
+        const int64_t tk = t0 + base + k;
+        Vec3 w, f;
+        if (G == 1) {
+          w = Vec3{smp.g[0], smp.g[1], smp.g[2]};
+          f = Vec3{smp.a[0], smp.a[1], smp.a[2]};
+        } else {
+          w = Vec3{shfl_grp<G>(smp.g[0], k), shfl_grp<G>(smp.g[1], k), shfl_grp<G>(smp.g[2], k)};
+          f = Vec3{shfl_grp<G>(smp.a[0], k), shfl_grp<G>(smp.a[1], k), shfl_grp<G>(smp.a[2], k)};
+        }
+        if (!FED) {
+          double zg[3], za[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            zg[c] = (G == 1) ? smp.zg[c] : shfl_grp<G>(smp.zg[c], k);
+            za[c] = (G == 1) ? smp.za[c] : shfl_grp<G>(smp.za[c], k);
+          }
+          // meas = ... + drift: d[t] (GM) or drift*z[t] (white drift), pathgen.py:583-593
+          w.x += dg[0] + p.gyro.wd[0] * zg[0];
+          w.y += dg[1] + p.gyro.wd[1] * zg[1];
+          w.z += dg[2] + p.gyro.wd[2] * zg[2];
+          f.x += da[0] + p.accel.wd[0] * za[0];
+          f.y += da[1] + p.accel.wd[1] * za[1];
+          f.z += da[2] + p.accel.wd[2] * za[2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {  // d[t+1] = a d[t] + b z[t]
+            dg[c] = p.gyro.gm_a[c] * dg[c] + p.gyro.gm_b[c] * zg[c];
+            da[c] = p.accel.gm_a[c] * da[c] + p.accel.gm_b[c] * za[c];
+          }
+        }
+        if (PROC) {
+          // error of sample tk (state BEFORE the step), ins_data_manager.py:536-541
+          if (tk >= p.stats_start) {
+            const double* r = &sm.nav[s][(base + k) * 9];
+            double e[9];
+            e[0] = angle_range_pi(st.yaw - r[0]);
+            e[1] = angle_range_pi(st.pitch - r[1]);
+            e[2] = angle_range_pi(st.roll - r[2]);
+            e[3] = st.pos.x - r[3];
+            e[4] = st.pos.y - r[4];
+            e[5] = st.pos.z - r[5];
+            e[6] = st.vel.x - r[6];
+            e[7] = st.vel.y - r[7];
+            e[8] = st.vel.z - r[8];
+            if (pe_cnt == 0) {
+#pragma unroll
+              for (int c = 0; c < 9; ++c) pe_k[c] = e[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+              pe_max[c] = fmax(pe_max[c], fabs(e[c]));
+              const double d = e[c] - pe_k[c];
+              pe_sum[c] += d;
+              pe_sq[c] += d * d;
+            }
+            ++pe_cnt;
+          }
+        }
+        if (j == k) {
+          keep[0] = w.x; keep[1] = w.y; keep[2] = w.z;
+          keep[3] = f.x; keep[4] = f.y; keep[5] = f.z;
+        }
+        if (tk < p.n - 1) {
+          nav_step<RF>(st, w, f, p.dt, p.earth_rot != 0);
+          if (j == k) {
+            keep[6] = st.yaw; keep[7] = st.pitch; keep[8] = st.roll;
+            keep[9] = st.pos.x; keep[10] = st.pos.y; keep[11] = st.pos.z;
+            keep[12] = st.vel.x; keep[13] = st.vel.y; keep[14] = st.vel.z;
+          }
+        }
+      }
+      // ---------------- histories: lane j writes sample base+j (meas) / +1 (state) --
+      if (dump && tj < cnt) {
+        if (p.out_gyro) {
+          const int64_t o = run * p.osr + t * p.ost;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            p.out_gyro[o + c * p.osc] = keep[c];
+            p.out_accel[o + c * p.osc] = keep[3 + c];
+          }
+        }
+        if (p.out_att && t + 1 < p.n) {
+          const int64_t o = run * p.osr + (t + 1) * p.ost;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            p.out_att[o + c * p.osc] = keep[6 + c];
+            p.out_pos[o + c * p.osc] = keep[9 + c];
+            p.out_vel[o + c * p.osc] = keep[12 + c];
+          }
+        }
+      }
+    }
+
+    if (kStaged) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[s]);
+      if (threadIdx.x == 0 && tile + kStages < num_tiles) {
+        mbar_wait(&sm.empty[s], parity);
+        issue_tile<FED, PROC>(sm, p, tile + kStages, s);
+      }
+    }
+  }
+
+  // ---- per-run results -----------------------------------------------------
+  if (active && j == 0) {
+    if (p.end_err) {
+      const double* r = p.ref_nav + (p.n - 1) * 9;
+      double* e = p.end_err + run * 9;
+      e[0] = angle_range_pi(st.yaw - r[0]);
+      e[1] = angle_range_pi(st.pitch - r[1]);
+      e[2] = angle_range_pi(st.roll - r[2]);
+      e[3] = st.pos.x - r[3];
+      e[4] = st.pos.y - r[4];
+      e[5] = st.pos.z - r[5];
+      e[6] = st.vel.x - r[6];
+      e[7] = st.vel.y - r[7];
+      e[8] = st.vel.z - r[8];
+    }
+    if (p.end_state) {
+      double* e = p.end_state + run * 9;
+      e[0] = st.yaw; e[1] = st.pitch; e[2] = st.roll;
+      e[3] = st.pos.x; e[4] = st.pos.y; e[5] = st.pos.z;
+      e[6] = st.vel.x; e[7] = st.vel.y; e[8] = st.vel.z;
+    }
+    if (PROC && p.proc_stats) {
+      double* o = p.proc_stats + run * 27;
+      const double inv = pe_cnt > 0 ? 1.0 / static_cast<double>(pe_cnt) : 0.0;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const double m = pe_sum[c] * inv;  // mean of (e - K)
+        o[c] = pe_max[c];
+        o[9 + c] = pe_k[c] + m;
+        o[18 + c] = sqrt(fmax(pe_sq[c] * inv - m * m, 0.0));
+      }
+    }
+  }
+}
+
+}  // namespace b2ins

@@ -1,0 +1,215 @@
+// Strapdown free-integration mechanization: the per-timestep recurrence of
+// FreeIntegration.run (demo_algorithms/free_integration.py:63-174) with the L1 math it
+// calls (attitude.py:344-371 euler2dcm zyx, :679-721 euler_update_zyx, :758-770 cross3;
+// geoparams.py:25-53 geo_param, :70-87 lla2ecef), written once for all kernels.
+// The whole state lives in registers; everything is double.
+#pragma once
+#include "common.cuh"
+
+namespace b2ins {
+
+struct Vec3 {
+  double x, y, z;
+};
+
+// n -> b direction cosine matrix, row-major
+struct Dcm {
+  double c00, c01, c02, c10, c11, c12, c20, c21, c22;
+};
+
+struct SinCos3 {
+  double sy, cy, sp, cp, sr, cr;  // yaw, pitch, roll
+};
+
+__device__ __forceinline__ SinCos3 sincos3(double yaw, double pitch, double roll) {
+  SinCos3 t;
+  sincos(yaw, &t.sy, &t.cy);
+  sincos(pitch, &t.sp, &t.cp);
+  sincos(roll, &t.sr, &t.cr);
+  return t;
+}
+
+// attitude.euler2dcm, 'zyx' branch: attitude.py:361-371
+__device__ __forceinline__ Dcm dcm_from_sincos(const SinCos3& t) {
+  Dcm c;
+  c.c00 = t.cp * t.cy;
+  c.c01 = t.cp * t.sy;
+  c.c02 = -t.sp;
+  c.c10 = t.sr * t.sp * t.cy - t.cr * t.sy;
+  c.c11 = t.sr * t.sp * t.sy + t.cr * t.cy;
+  c.c12 = t.cp * t.sr;
+  c.c20 = t.sp * t.cr * t.cy + t.sy * t.sr;
+  c.c21 = t.sp * t.cr * t.sy - t.cy * t.sr;
+  c.c22 = t.cp * t.cr;
+  return c;
+}
+
+__device__ __forceinline__ Vec3 mul(const Dcm& c, const Vec3& v) {  // c . v
+  return Vec3{c.c00 * v.x + c.c01 * v.y + c.c02 * v.z, c.c10 * v.x + c.c11 * v.y + c.c12 * v.z,
+              c.c20 * v.x + c.c21 * v.y + c.c22 * v.z};
+}
+__device__ __forceinline__ Vec3 mul_t(const Dcm& c, const Vec3& v) {  // c^T . v
+  return Vec3{c.c00 * v.x + c.c10 * v.y + c.c20 * v.z, c.c01 * v.x + c.c11 * v.y + c.c21 * v.z,
+              c.c02 * v.x + c.c12 * v.y + c.c22 * v.z};
+}
+// attitude.cross3: attitude.py:758-770
+__device__ __forceinline__ Vec3 cross3(const Vec3& a, const Vec3& b) {
+  return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// geoparams.geo_param: geoparams.py:25-53
+struct GeoParam {
+  double rm, rn, g, sl, cl;
+};
+__device__ __forceinline__ GeoParam geo_param(double lat, double h) {
+  GeoParam p;
+  sincos(lat, &p.sl, &p.cl);
+  const double sl_sqr = p.sl * p.sl;
+  const double q = 1.0 - kESqr * sl_sqr;
+  const double sq = sqrt(q);
+  p.rm = (kRe * (1 - kESqr)) / (sq * q);
+  p.rn = kRe / sq;
+  const double g1 = kNormalGravity * (1 + kGravK * sl_sqr) / sq;
+  p.g = g1 * (1.0 - (2.0 / kRe) * (1.0 + kFlat + kGravM - 2.0 * kFlat * sl_sqr) * h +
+              3.0 * h * h / kRe / kRe);
+  return p;
+}
+
+// geoparams.lla2ecef: geoparams.py:70-87
+__device__ __forceinline__ Vec3 lla2ecef(double lat, double lon, double alt) {
+  double sl, cl, so, co;
+  sincos(lat, &sl, &cl);
+  sincos(lon, &so, &co);
+  const double r = kRe / sqrt(1.0 - kESqr * sl * sl);
+  const double rho = (r + alt) * cl;
+  return Vec3{rho * co, rho * so, (r * (1.0 - kESqr) + alt) * sl};
+}
+
+// attitude.angle_range_pi: attitude.py:799-812 (python float % : result has the sign of 2pi)
+__device__ __forceinline__ double angle_range_pi(double x) {
+  double m = fmod(x, kTwoPi);
+  if (m < 0.0) m += kTwoPi;
+  if (m > kPi) m -= kTwoPi;
+  return m;
+}
+
+// The navigation state of one Monte-Carlo run.
+struct NavState {
+  double yaw, pitch, roll;
+  SinCos3 sc;  // sin/cos of (yaw, pitch, roll): euler2dcm(att[i]) of step i IS the
+               // cos/sin euler_update_zyx needs at step i+1, so it is computed once
+  Vec3 vel_b;  // body velocity   (ref_frame 1 state)
+  Vec3 vel;    // NED velocity    (ref_frame 0 state; ref_frame 1 output)
+  Vec3 pos;    // ECEF-offset xyz (ref_frame 1) or lat, lon, alt (ref_frame 0)
+  double g;    // gravity: geo_param(r0) or the ini override
+  bool fixed_g;  // false: ref_frame 0 without override -> geo_param(pos) every step
+};
+
+// free_integration.py:96-102 / :126-132 -- sample 0
+template <int RF>
+__device__ __forceinline__ void nav_init(NavState& s, const double* __restrict__ ini,
+                                         int ini_rows) {
+  const double lat = ini[0], lon = ini[1], alt = ini[2];
+  s.vel_b = Vec3{ini[3], ini[4], ini[5]};
+  s.yaw = ini[6];
+  s.pitch = ini[7];
+  s.roll = ini[8];
+  s.sc = sincos3(s.yaw, s.pitch, s.roll);
+  const Dcm c = dcm_from_sincos(s.sc);
+  s.vel = mul_t(c, s.vel_b);
+  if (RF == 1) {
+    s.pos = lla2ecef(lat, lon, alt);
+    s.g = (ini_rows > 9) ? ini[9] : geo_param(lat, alt).g;  // free_integration.py:89-93
+    s.fixed_g = true;
+  } else {
+    s.pos = Vec3{lat, lon, alt};
+    s.fixed_g = ini_rows > 9;  // free_integration.py:143-146
+    s.g = s.fixed_g ? ini[9] : 0.0;
+  }
+}
+
+// attitude.euler_update_zyx (attitude.py:679-721) using the cached sin/cos of the
+// current angles.  t*tan(pitch) is evaluated as (t/cos(pitch))*sin(pitch).
+__device__ __forceinline__ void euler_update(NavState& s, const Vec3& w, double dt) {
+  const double t = w.z * s.sc.cr + w.y * s.sc.sr;
+  const double phi_dot = t / s.sc.cp;
+  const double theta_dot = w.y * s.sc.cr - w.z * s.sc.sr;
+  const double psi_dot = w.x + phi_dot * s.sc.sp;
+  double y0 = s.yaw + phi_dot * dt;
+  double y1 = s.pitch + theta_dot * dt;
+  double y2 = s.roll + psi_dot * dt;
+  if (y1 > kHalfPi) {
+    y1 = kPi - y1;
+    y0 += kPi;
+    y2 += kPi;
+  } else if (y1 < -kHalfPi) {
+    y1 = -kPi - y1;
+    y0 += kPi;
+    y2 += kPi;
+  }
+  if (y0 > kPi)
+    y0 -= kTwoPi;
+  else if (y0 < -kPi)
+    y0 += kTwoPi;
+  if (y2 > kPi)
+    y2 -= kTwoPi;
+  else if (y2 < -kPi)
+    y2 += kTwoPi;
+  s.yaw = y0;
+  s.pitch = y1;
+  s.roll = y2;
+}
+
+// One step i-1 -> i with the measurements of sample i-1.
+template <int RF>
+__device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel,
+                                         double dt, bool earth_rot) {
+  if (RF == 1) {
+    // free_integration.py:104-116
+    // c_bn.dot(g_n) with g_n = [0,0,g]: third column of the OLD dcm, from the old sin/cos
+    const Vec3 cg{-s.sc.sp * s.g, s.sc.cp * s.sc.sr * s.g, s.sc.cp * s.sc.cr * s.g};
+    const Vec3 wxv = cross3(gyro, s.vel_b);
+    const Vec3 vel_old = s.vel;
+    euler_update(s, gyro, dt);
+    s.vel_b.x = s.vel_b.x + (accel.x + cg.x) * dt - wxv.x * dt;
+    s.vel_b.y = s.vel_b.y + (accel.y + cg.y) * dt - wxv.y * dt;
+    s.vel_b.z = s.vel_b.z + (accel.z + cg.z) * dt - wxv.z * dt;
+    s.sc = sincos3(s.yaw, s.pitch, s.roll);
+    const Dcm c = dcm_from_sincos(s.sc);
+    s.vel = mul_t(c, s.vel_b);
+    s.pos.x += vel_old.x * dt;
+    s.pos.y += vel_old.y * dt;
+    s.pos.z += vel_old.z * dt;
+  } else {
+    // free_integration.py:133-172
+    const GeoParam p = geo_param(s.pos.x, s.pos.z);
+    const double rm_e = p.rm + s.pos.z;
+    const double rn_e = p.rn + s.pos.z;
+    const double g = s.fixed_g ? s.g : p.g;
+    const Vec3 w_en{s.vel.y / rn_e, -s.vel.x / rm_e, -s.vel.y * p.sl / p.cl / rn_e};
+    Vec3 w_ie{0.0, 0.0, 0.0};
+    if (earth_rot) {
+      w_ie.x = kWie * p.cl;
+      w_ie.z = -kWie * p.sl;
+    }
+    const Dcm c = dcm_from_sincos(s.sc);  // c_bn of step i-1
+    const Vec3 w_sum{w_en.x + w_ie.x, w_en.y + w_ie.y, w_en.z + w_ie.z};
+    const Vec3 cw = mul(c, w_sum);
+    const Vec3 w_nb{gyro.x - cw.x, gyro.y - cw.y, gyro.z - cw.z};
+    const Vec3 fa = mul_t(c, accel);
+    const Vec3 w2{2 * w_ie.x + w_en.x, 2 * w_ie.y + w_en.y, 2 * w_ie.z + w_en.z};
+    const Vec3 cor = cross3(w2, s.vel);
+    const Vec3 vel_old = s.vel;
+    euler_update(s, w_nb, dt);
+    s.vel.x = vel_old.x + (fa.x - cor.x) * dt;
+    s.vel.y = vel_old.y + (fa.y - cor.y) * dt;
+    s.vel.z = vel_old.z + (fa.z + g - cor.z) * dt;
+    s.pos.x += vel_old.x / rm_e * dt;
+    s.pos.y += vel_old.y / rn_e / p.cl * dt;
+    s.pos.z += (-vel_old.z) * dt;
+    s.sc = sincos3(s.yaw, s.pitch, s.roll);
+    // vel_b[i] = c_bn(i).dot(vel[i]) (:172) is not an output of the plugin; not computed
+  }
+}
+
+}  // namespace b2ins

@@ -1,0 +1,136 @@
+// K1: IMU sensor-error generator, materialised -- pathgen.acc_gen / gyro_gen / bias_drift
+// (pathgen.py:441-594).  Time-parallel: one CTA per run walks the samples in tiles of
+// kNoiseThreads; thread i draws the normals of sample tile0+i (Philox4x32-10, Box-Muller),
+// the first-order Gauss-Markov drift d[t+1] = a d[t] + b z[t] is an affine block scan
+// (warp shuffles + one shared-memory hop) with the carry kept across tiles, and the
+// measurements are written with the caller's strides.
+#pragma once
+#include "mc_kernel.cuh"
+
+namespace b2ins {
+
+constexpr int kNoiseThreads = 256;
+constexpr int kNoiseWarps = kNoiseThreads / 32;
+
+struct NoiseParams {
+  int64_t n, runs, run_offset;
+  double dt;
+  uint32_t k0, k1;
+  TriadNoise gyro, accel;
+  const double* ref_gyro;
+  const double* ref_accel;
+  double* out_gyro;
+  double* out_accel;
+  int64_t osr, ost, osc;
+  double* z_dump;  // [runs][n][12] or null
+};
+
+// inclusive scan of y_i = a y_{i-1} + x_i over the block (zero initial state).
+// apow[k] = a^k for k = 0..kNoiseThreads.  Returns y_i; *total = y_last (all threads).
+__device__ __forceinline__ double gm_block_scan(double x, const double* apow, double* sh_w,
+                                                double* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v = x;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double u = __shfl_up_sync(0xffffffffu, v, off);
+    if (lane >= off) v += apow[off] * u;
+  }
+  if (lane == 31) sh_w[warp] = v;
+  __syncthreads();
+  // prefix over previous warps: P_w = sum_{q<w} a^{32 (w-1-q)} W_q
+  double pre = 0.0;
+  for (int q = 0; q < warp; ++q) pre = apow[32] * pre + sh_w[q];
+  double tot = 0.0;
+  for (int q = 0; q < kNoiseWarps; ++q) tot = apow[32] * tot + sh_w[q];
+  *total = tot;
+  __syncthreads();
+  return v + apow[lane + 1] * pre;
+}
+
+__global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
+  __shared__ double apow[6][kNoiseThreads + 1];
+  __shared__ double sh_w[kNoiseWarps];
+  const int64_t run = blockIdx.x;
+  const int64_t grun = p.run_offset + run;
+  const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
+  const int i = threadIdx.x;
+  for (int k = threadIdx.x; k <= kNoiseThreads; k += kNoiseThreads) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      apow[c][k] = pow(p.accel.gm_a[c], static_cast<double>(k));
+      apow[3 + c][k] = pow(p.gyro.gm_a[c], static_cast<double>(k));
+    }
+  }
+  double phase[3] = {0.0, 0.0, 0.0};
+  if (p.gyro.vib_type == 2) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      phase[c] = (uniform01(0xFFFFFFFFu, kDrawPhase + c, run_lo, run_hi, p.k0, p.k1) * 2.0) * kPi;
+  }
+  double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // d at the first sample of the tile
+  __syncthreads();
+
+  for (int64_t tile0 = 0; tile0 < p.n; tile0 += kNoiseThreads) {
+    const int64_t t = tile0 + i;
+    const bool live = t < p.n;
+    double m[6], z[6];
+    if (live) {
+      noisy_triad(p.accel, p.ref_accel + t * 3, static_cast<uint32_t>(t), kDrawAccel, 0, run_lo,
+                  run_hi, p.k0, p.k1, run, phase, m, z);
+      noisy_triad(p.gyro, p.ref_gyro + t * 3, static_cast<uint32_t>(t), kDrawGyro, 1, run_lo,
+                  run_hi, p.k0, p.k1, run, phase, m + 3, z + 3);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) m[c] = z[c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const TriadNoise& e = (c < 3) ? p.accel : p.gyro;
+      const int a = c % 3;
+      // y_i = sum_{q<=i} a^{i-q} b z_q  ->  d[tile0+i+1] = a^{i+1} carry + y_i
+      double total;
+      const double y = gm_block_scan(e.gm_b[a] * z[c], apow[c], sh_w, &total);
+      const double y_prev = __shfl_up_sync(0xffffffffu, y, 1);
+      // d[tile0 + i]: needs y_{i-1}; lane 0 of a warp takes it from the previous warp
+      __shared__ double sh_last[kNoiseWarps];
+      if ((threadIdx.x & 31) == 31) sh_last[threadIdx.x >> 5] = y;
+      __syncthreads();
+      double ym1;
+      if (i == 0)
+        ym1 = 0.0;
+      else if ((threadIdx.x & 31) == 0)
+        ym1 = sh_last[(threadIdx.x >> 5) - 1];
+      else
+        ym1 = y_prev;
+      const double d = apow[c][i] * carry[c] + ym1;
+      m[c] += d + e.wd[a] * z[c];
+      carry[c] = apow[c][kNoiseThreads] * carry[c] + total;
+      __syncthreads();
+    }
+    if (live) {
+      const int64_t o = run * p.osr + t * p.ost;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        p.out_accel[o + c * p.osc] = m[c];
+        p.out_gyro[o + c * p.osc] = m[3 + c];
+      }
+      if (p.z_dump) {
+        // (acc_gm[3], acc_w[3], gyr_gm[3], gyr_w[3]); the white normals are recovered from
+        // the same Philox draws
+        double* zd = p.z_dump + (run * p.n + t) * 12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const Normal2 za = normal_pair(static_cast<uint32_t>(t), kDrawAccel + c, run_lo, run_hi, p.k0, p.k1);
+          const Normal2 zg = normal_pair(static_cast<uint32_t>(t), kDrawGyro + c, run_lo, run_hi, p.k0, p.k1);
+          zd[c] = za.z0;
+          zd[3 + c] = za.z1;
+          zd[6 + c] = zg.z0;
+          zd[9 + c] = zg.z1;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace b2ins

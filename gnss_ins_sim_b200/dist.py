@@ -1,0 +1,136 @@
+"""Multi-GPU plumbing: Monte-Carlo runs shard embarrassingly across ranks (one process
+per GPU, torch.distributed); the only data-path collectives are one broadcast of the
+CPU-generated trajectory and the all-reduces of the final error statistics
+(SURVEY 8e).  Works un-initialised (single process) and with the gloo backend (CPU
+tests of the host logic); on GPUs the backend is NCCL over NVLink.
+
+Statistics are combined exactly like np.std's two passes:
+  phase 1  all-reduce SUM(sum e, count), MAX(max|e|)  -> mean
+  phase 2  all-reduce SUM(sum (e-mean)^2)             -> std (ddof 0)
+"""
+import numpy as np
+import torch
+import torch.distributed as td
+
+
+def initialised():
+    return td.is_available() and td.is_initialized()
+
+
+def rank():
+    return td.get_rank() if initialised() else 0
+
+
+def world():
+    return td.get_world_size() if initialised() else 1
+
+
+def shard(total, r=None, w=None):
+    """Contiguous block [lo, hi) of `total` runs owned by rank r of w (first ranks take the
+    remainder).  Global run ids are rank-independent, so results do not depend on w."""
+    r = rank() if r is None else r
+    w = world() if w is None else w
+    base, rem = divmod(int(total), w)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+def _comm_device():
+    if initialised() and td.get_backend() == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def all_reduce(t, op):
+    """all-reduce a tensor in place on the backend's device; returns it on its own device."""
+    if not initialised():
+        return t
+    dev = _comm_device()
+    buf = t if t.device == dev else t.to(dev)
+    td.all_reduce(buf, op=op)
+    if buf is not t:
+        t.copy_(buf)
+    return t
+
+
+def combine_phase1(partial, local_runs, ncomp):
+    """partial [2*ncomp] = (sum e, max|e|) of this rank (zeros if it owns no runs).
+    Returns (mean [ncomp], max [ncomp], total_runs) after the all-reduces."""
+    sums = torch.cat([partial[:ncomp], partial.new_tensor([float(local_runs)])])
+    mx = partial[ncomp:2 * ncomp].clone()
+    all_reduce(sums, td.ReduceOp.SUM)
+    all_reduce(mx, td.ReduceOp.MAX)
+    total = float(sums[ncomp].item())
+    return sums[:ncomp] / total, mx, int(round(total))
+
+
+def combine_phase2(partial2, total_runs):
+    """partial2 [ncomp] = sum (e - mean)^2 of this rank -> std [ncomp]."""
+    p = partial2.clone()
+    all_reduce(p, td.ReduceOp.SUM)
+    return torch.sqrt(p / float(total_runs))
+
+
+def ensemble_stats(end_err, total_runs):
+    """[3, ncomp] numpy = max|e|, mean, std over ALL ranks' runs.
+    end_err: this rank's CUDA [R_local, ncomp] (or None if it owns no runs)."""
+    from . import engine
+    ncomp = 9 if end_err is None else end_err.shape[1]
+    dev = end_err.device if end_err is not None else _comm_device()
+    if end_err is not None and end_err.shape[0] > 0:
+        partial = engine.error_partial(end_err)
+        local = end_err.shape[0]
+    else:
+        partial = torch.zeros(2 * ncomp, dtype=torch.float64, device=dev)
+        local = 0
+    mean, mx, total = combine_phase1(partial, local, ncomp)
+    assert total == total_runs, (total, total_runs)
+    if local:
+        partial2 = engine.error_partial2(end_err, mean)
+    else:
+        partial2 = torch.zeros(ncomp, dtype=torch.float64, device=dev)
+    std = combine_phase2(partial2, total)
+    return torch.stack([mx, mean, std]).cpu().numpy()
+
+
+def gather_rows(local, total_runs):
+    """Concatenate per-rank row blocks [R_local, C] (shard() order) -> numpy [total, C] on
+    every rank.  Blocks are padded to the largest shard for the all_gather."""
+    if not initialised():
+        return local.cpu().numpy()
+    w = world()
+    sizes = [shard(total_runs, r, w) for r in range(w)]
+    cap = max(hi - lo for lo, hi in sizes)
+    cols = torch.tensor([0 if local is None else local.shape[1]], dtype=torch.int64,
+                        device=_comm_device())
+    all_reduce(cols, td.ReduceOp.MAX)
+    C = int(cols.item())
+    dev = _comm_device()
+    pad = torch.zeros((cap, C), dtype=torch.float64, device=dev)
+    if local is not None and local.shape[0]:
+        pad[:local.shape[0]] = local.to(dev)
+    outs = [torch.empty_like(pad) for _ in range(w)]
+    td.all_gather(outs, pad)
+    return np.concatenate([o[:hi - lo].cpu().numpy() for o, (lo, hi) in zip(outs, sizes)], axis=0)
+
+
+def broadcast_trajectory(traj, src=0):
+    """Rank `src` holds the CPU-generated trajectory dict of (n,3) arrays; everyone gets it."""
+    if not initialised():
+        return traj
+    names = ['ref_pos', 'ref_vel', 'ref_att', 'ref_accel', 'ref_gyro']
+    dev = _comm_device()
+    n = torch.tensor([traj['ref_gyro'].shape[0] if rank() == src else 0], dtype=torch.int64,
+                     device=dev)
+    td.broadcast(n, src)
+    buf = torch.empty((int(n.item()), 15), dtype=torch.float64, device=dev)
+    if rank() == src:
+        buf.copy_(torch.from_numpy(np.concatenate([traj[k] for k in names], axis=1)))
+    td.broadcast(buf, src)
+    host = buf.cpu().numpy()
+    out = {k: np.ascontiguousarray(host[:, 3 * i:3 * i + 3]) for i, k in enumerate(names)}
+    if traj is not None:
+        for k in ('time', 'ini'):
+            if k in traj:
+                out[k] = traj[k]
+    return out

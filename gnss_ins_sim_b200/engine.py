@@ -1,0 +1,232 @@
+"""Device-level Python API over the C ABI (include/b2ins.h).
+
+PyTorch is plumbing here: it owns device memory (float64 CUDA tensors) and the current
+stream; every kernel is in csrc/libb2ins.so.  All functions are asynchronous on the
+current torch stream unless they return host data.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_RUN_MAJOR, LAYOUT_TIME_MAJOR  # noqa: F401
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.B2insError('no CUDA device: the b2ins engine has no CPU fallback')
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), 'need contiguous cuda f64'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def to_device(a, device=None):
+    """numpy / tensor -> contiguous float64 CUDA tensor (H2D copy if needed)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device or 'cuda', dtype=torch.float64).contiguous()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return torch.from_numpy(a).to(device or 'cuda')
+
+
+def ini_sets_from_plugin(ini_pos_vel_att):
+    """FreeIntegration's ini_pos_vel_att ((9|10,) or (9|10, S)) -> [S][rows] row-major."""
+    a = np.asarray(ini_pos_vel_att, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    elif a.ndim != 2:
+        raise ValueError('Initial states should be a 1D or 2D numpy array, '
+                         'but the dimension is %s.' % a.ndim)
+    if a.shape[0] not in (9, 10):
+        raise ValueError('Initial states need 9 (or 10 with gravity) rows, got %d' % a.shape[0])
+    return np.ascontiguousarray(a.T)
+
+
+def free_integration(ref_frame, fs, gyro, accel, ini, earth_rot=True, layout=LAYOUT_RUN_MAJOR,
+                     run_offset=0, lanes_per_run=0):
+    """K2.  gyro, accel: CUDA f64 [R,n,3] (RUN_MAJOR) or [n,3,R] (TIME_MAJOR);
+    ini: CUDA f64 [S,9|10].  Returns att, pos, vel in the same layout."""
+    _require_cuda()
+    lib = _lib.load()
+    if layout == LAYOUT_RUN_MAJOR:
+        R, n, three = gyro.shape
+    else:
+        n, three, R = gyro.shape
+    assert three == 3 and gyro.shape == accel.shape
+    att = torch.empty_like(gyro)
+    pos = torch.empty_like(gyro)
+    vel = torch.empty_like(gyro)
+    _lib.check(lib.b2ins_free_integration_f64(
+        int(ref_frame), float(fs), R, n, _ptr(gyro), _ptr(accel), layout, _ptr(ini),
+        ini.shape[0], ini.shape[1], int(run_offset), int(bool(earth_rot)),
+        _ptr(att), _ptr(pos), _ptr(vel), int(lanes_per_run), _stream()))
+    return att, pos, vel
+
+
+def imu_noise(fs, runs, ref_gyro, ref_accel, gyro_err, accel_err, seed, run_offset=0,
+              vib_gyro=None, vib_accel=None, layout=LAYOUT_RUN_MAJOR, dump_z=False):
+    """K1.  ref_gyro/ref_accel: CUDA f64 [n,3]; *_err: imu_model dicts.
+    Returns gyro, accel ([R,n,3] or [n,3,R]) and, if dump_z, z [R,n,12]."""
+    _require_cuda()
+    lib = _lib.load()
+    n = ref_gyro.shape[0]
+    shape = (runs, n, 3) if layout == LAYOUT_RUN_MAJOR else (n, 3, runs)
+    gyro = torch.empty(shape, dtype=torch.float64, device=ref_gyro.device)
+    accel = torch.empty_like(gyro)
+    z = torch.empty((runs, n, 12), dtype=torch.float64, device=ref_gyro.device) if dump_z else None
+    ge, ae = _lib.sensor_err(gyro_err, 'arw'), _lib.sensor_err(accel_err, 'vrw')
+    vg, va = _lib.vib(vib_gyro), _lib.vib(vib_accel)
+    _lib.check(lib.b2ins_imu_noise_f64(
+        float(fs), runs, n, _ptr(ref_gyro), _ptr(ref_accel), ctypes.byref(ge), ctypes.byref(ae),
+        ctypes.byref(vg), ctypes.byref(va), int(seed), int(run_offset), layout,
+        _ptr(gyro), _ptr(accel), _ptr(z), _stream()))
+    return (gyro, accel, z) if dump_z else (gyro, accel)
+
+
+class McResult:
+    """Device-side results of one fused Monte-Carlo launch."""
+
+    def __init__(self):
+        self.end_err = None      # [R,9] att(wrapped),pos,vel error at the last sample
+        self.end_state = None    # [R,9]
+        self.proc_stats = None   # [R,3,9] max|e|, mean, std per run (stats_start >= 0)
+        self.att = self.pos = self.vel = None   # [dump_runs,n,3]
+        self.gyro = self.accel = None           # [dump_runs,n,3]
+        self.lanes_per_run = 0
+
+
+def make_mc_config(ref_frame, fs, n, runs, seed, gyro_err, accel_err, ini_sets, ini_rows,
+                   earth_rot=True, run_offset=0, vib_gyro=None, vib_accel=None,
+                   lanes_per_run=0, stats_start=-1, dump_runs=0, ini_offset=None):
+    cfg = _lib.McConfig()
+    cfg.ref_frame = int(ref_frame)
+    cfg.earth_rot = int(bool(earth_rot))
+    cfg.fs = float(fs)
+    cfg.n = int(n)
+    cfg.runs = int(runs)
+    cfg.run_offset = int(run_offset)
+    cfg.ini_offset = int(run_offset if ini_offset is None else ini_offset)
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.gyro_err = _lib.sensor_err(gyro_err, 'arw')
+    cfg.accel_err = _lib.sensor_err(accel_err, 'vrw')
+    cfg.vib_gyro = vib_gyro if isinstance(vib_gyro, _lib.Vib) else _lib.vib(vib_gyro)
+    cfg.vib_accel = vib_accel if isinstance(vib_accel, _lib.Vib) else _lib.vib(vib_accel)
+    cfg.ini_sets = int(ini_sets)
+    cfg.ini_rows = int(ini_rows)
+    cfg.lanes_per_run = int(lanes_per_run)
+    cfg.stats_start = int(stats_start)
+    cfg.dump_runs = int(dump_runs)
+    return cfg
+
+
+def mc_free_integration(cfg, ref_gyro, ref_accel, ref_nav, ini, want_state=False,
+                        dump_nav=False, dump_imu=False, out=None):
+    """K12: fused noise generation + free integration + per-run errors.
+    ref_gyro, ref_accel [n,3]; ref_nav [n,9] (att,pos,vel); ini [S,rows]: CUDA f64.
+    `out` may carry a preallocated McResult to reuse buffers."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = ref_gyro.device
+    R, n, D = cfg.runs, cfg.n, cfg.dump_runs
+    res = out or McResult()
+
+    def buf(cur, shape):
+        if cur is not None and tuple(cur.shape) == tuple(shape):
+            return cur
+        return torch.empty(shape, dtype=torch.float64, device=dev)
+
+    res.end_err = buf(res.end_err, (R, 9))
+    res.end_state = buf(res.end_state, (R, 9)) if want_state else None
+    res.proc_stats = buf(res.proc_stats, (R, 3, 9)) if cfg.stats_start >= 0 else None
+    if dump_nav and D > 0:
+        res.att, res.pos, res.vel = (buf(res.att, (D, n, 3)), buf(res.pos, (D, n, 3)),
+                                     buf(res.vel, (D, n, 3)))
+    else:
+        res.att = res.pos = res.vel = None
+    if dump_imu and D > 0:
+        res.gyro, res.accel = buf(res.gyro, (D, n, 3)), buf(res.accel, (D, n, 3))
+    else:
+        res.gyro = res.accel = None
+    _lib.check(lib.b2ins_mc_free_integration_f64(
+        ctypes.byref(cfg), _ptr(ref_gyro), _ptr(ref_accel), _ptr(ref_nav), _ptr(ini),
+        _ptr(res.end_err), _ptr(res.end_state), _ptr(res.proc_stats),
+        _ptr(res.att), _ptr(res.pos), _ptr(res.vel), _ptr(res.gyro), _ptr(res.accel), _stream()))
+    return res
+
+
+_ws_cache = {}
+
+
+def _stats_ws(ncomp, dev):
+    key = (ncomp, str(dev))
+    if key not in _ws_cache:
+        nbytes = _lib.load().b2ins_error_stats_workspace_bytes(ncomp)
+        _ws_cache[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=dev)
+    return _ws_cache[key]
+
+
+def error_stats(err):
+    """K3 on one shard.  err: CUDA f64 [R, ncomp] -> stats [3, ncomp] = max|e|, mean, std."""
+    _require_cuda()
+    lib = _lib.load()
+    R, nc = err.shape
+    stats = torch.empty((3, nc), dtype=torch.float64, device=err.device)
+    _lib.check(lib.b2ins_error_stats_f64(R, nc, _ptr(err), _ptr(stats),
+                                         _ptr(_stats_ws(nc, err.device)), _stream()))
+    return stats
+
+
+def error_partial(err):
+    """K3 phase 1: [2*ncomp] = (sum e, max|e|) of this shard."""
+    lib = _lib.load()
+    R, nc = err.shape
+    out = torch.empty(2 * nc, dtype=torch.float64, device=err.device)
+    _lib.check(lib.b2ins_error_partial_f64(R, nc, _ptr(err), _ptr(out),
+                                           _ptr(_stats_ws(nc, err.device)), _stream()))
+    return out
+
+
+def error_partial2(err, mean):
+    """K3 phase 2: [ncomp] = sum (e - mean)^2 of this shard."""
+    lib = _lib.load()
+    R, nc = err.shape
+    out = torch.empty(nc, dtype=torch.float64, device=err.device)
+    _lib.check(lib.b2ins_error_partial2_f64(R, nc, _ptr(err), _ptr(mean.contiguous()), _ptr(out),
+                                            _ptr(_stats_ws(nc, err.device)), _stream()))
+    return out
+
+
+def allan_num_tau(n, fs):
+    lib = _lib.load()
+    m = (ctypes.c_int64 * 128)()
+    k = lib.b2ins_allan_num_tau(int(n), float(fs), m, 128)
+    return list(m[:k])
+
+
+def allan(fs, x, n, nseries, inner=1, outer_stride=None, sample_stride=1):
+    """K4.  x: CUDA f64 buffer holding `nseries` series of n samples; series s, sample t at
+    x.flat[(s // inner) * outer_stride + (s % inner) + t * sample_stride].
+    Returns avar [nseries, ntau], tau [ntau] (CUDA)."""
+    _require_cuda()
+    lib = _lib.load()
+    if outer_stride is None:
+        outer_stride = n * sample_stride if inner == 1 else n * inner
+    ntau = len(allan_num_tau(n, fs))
+    avar = torch.zeros((nseries, ntau), dtype=torch.float64, device=x.device)
+    tau = torch.zeros((ntau,), dtype=torch.float64, device=x.device)
+    if ntau == 0 or nseries == 0:
+        return avar, tau
+    ws = torch.empty(lib.b2ins_allan_workspace_bytes(n, nseries) // 8 + 1, dtype=torch.float64,
+                     device=x.device)
+    _lib.check(lib.b2ins_allan_f64(float(fs), int(n), int(nseries), _ptr(x), int(inner),
+                                   int(outer_stride), int(sample_stride), _ptr(avar), _ptr(tau),
+                                   _ptr(ws), _stream()))
+    return avar, tau

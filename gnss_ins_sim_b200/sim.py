@@ -1,0 +1,606 @@
+"""Sim -- Monte-Carlo simulation facade with the interface of gnss_ins_sim.sim.ins_sim.Sim
+(ins_sim.py:27-337: same constructor arguments, run(num_times), results(...),
+get_data(names), the same data names / run keys / units), whose Monte-Carlo loops
+(loop A ins_sim.py:490-506, loop B ins_algo_manager.py:73-95) run as CUDA kernels.
+
+What stays on the CPU, by design (BASELINE north_star: "pathgen.path_gen stays CPU-side
+and its reference trajectory is broadcast once"): the true trajectory.  `motion_def` is
+  * a trajectory: dict / .npz path with time, ref_pos, ref_vel, ref_att, ref_accel,
+    ref_gyro (what pathgen.path_gen returns, e.g. tests/golden/traj_*.npz), or
+  * a motion-definition .csv / string exactly as the reference takes it; it is turned
+    into a trajectory by gnss_ins_sim.pathgen.path_gen, which therefore has to be
+    importable (pip install gnss-ins-sim); nothing else of the reference is used.
+
+Dispatch on `algorithm`:
+  * gnss_ins_sim_b200 FreeIntegration  -> K12, the fused noise+integration+error kernel;
+    only per-run end-point errors, their ensemble statistics (and, on request, per-run
+    process-error statistics) leave the device.  Per-run histories are materialised
+    lazily: counter-based Philox makes any run reproducible in isolation, so
+    get_data(['pos'])[0]['algo0_7'] re-runs just run 7 with history output on.
+  * gnss_ins_sim_b200 Allan            -> K1 (noise) + K4 (Allan variance) per run block.
+  * any other reference-style plugin   -> K1 generates gyro/accel on the device, the
+    plugin's own .run() is called per run on the host (compatibility path).
+  * None                               -> sensor data only.
+Multi-GPU: runs are sharded by rank when torch.distributed is initialised (dist.py).
+"""
+import math
+import os
+from collections.abc import Mapping
+
+import numpy as np
+import torch
+
+from . import engine, dist
+from .free_integration import FreeIntegration
+from .allan_analysis import Allan
+
+D2R = math.pi / 180
+R2D = 180 / math.pi
+_RE = 6378137.0
+_E_SQR = 0.0818191908426215 ** 2
+
+
+# ------------------------------------------------------------------ helpers ---
+def parse_env(env, fs):
+    """Vibration DSL -> dict, as Sim.__parse_env (ins_sim.py:642-701):
+    '[x y z](g|d)-random', '[x y z](g|d)-<f>Hz-sinusoidal', or (n,4) PSD array."""
+    if env is None:
+        return None
+    if isinstance(env, np.ndarray):
+        if env.ndim == 2 and env.shape[1] == 4:
+            m = env.shape[0]
+            if env[-1, 0] > 0.5 * fs:
+                m = np.where(env[:, 0] > 0.5 * fs)[0][0]
+            return {'type': 'psd', 'freq': env[:m, 0], 'x': env[:m, 1], 'y': env[:m, 2],
+                    'z': env[:m, 3]}
+        raise TypeError('env should be of size (n,2)')
+    if not isinstance(env, str):
+        raise TypeError('env should be a string or a numpy array of size (n,2)')
+    text = env.lower()
+    out = {}
+    if 'random' in text:
+        out['type'] = 'random'
+        text = text.replace('-random', '')
+    elif 'sinusoidal' in text:
+        out['type'] = 'sinusoidal'
+        text = text.replace('-sinusoidal', '')
+        if text[-2:] != 'hz':
+            raise ValueError('env = \'%s\' is not valid (No vib freq).' % env)
+        cut = text.find('-')
+        try:
+            out['freq'] = math.fabs(float(text[cut + 1:-2]))
+        except ValueError:
+            raise ValueError('env = \'%s\' is not valid (invalid vib freq).' % env)
+        text = text[:cut]
+    else:
+        raise ValueError('env = \'%s\' is not valid.' % env)
+    scale = 1.0
+    if text[-1] == 'g':
+        scale, text = 9.8, text[:-1]
+    elif text[-1] == 'd':
+        scale, text = D2R, text[:-1]
+    try:
+        amp = scale * np.array(text[1:-1].split(' '), dtype='float64')
+        out['x'], out['y'], out['z'] = amp[0], amp[1], amp[2]
+    except (ValueError, IndexError):
+        raise ValueError('Cannot convert \'%s\' to float' % env)
+    return out
+
+
+def lla2ecef(lla):
+    """geoparams.lla2ecef_batch (geoparams.py:89-113), host side, for 'ned' error option."""
+    lla = np.atleast_2d(np.asarray(lla, dtype=np.float64))
+    sl, cl = np.sin(lla[:, 0]), np.cos(lla[:, 0])
+    r = _RE / np.sqrt(1.0 - _E_SQR * sl * sl)
+    rho = (r + lla[:, 2]) * cl
+    return np.stack([rho * np.cos(lla[:, 1]), rho * np.sin(lla[:, 1]),
+                     (r * (1.0 - _E_SQR) + lla[:, 2]) * sl], axis=1)
+
+
+def ecef_to_ned(lat, lon):
+    """attitude.ecef_to_ned (attitude.py: c_ne), rotation ECEF -> local NED."""
+    sl, cl, so, co = math.sin(lat), math.cos(lat), math.sin(lon), math.cos(lon)
+    return np.array([[-sl * co, -sl * so, cl], [-so, co, 0.0], [-cl * co, -cl * so, -sl]])
+
+
+def load_trajectory(src):
+    """dict / npz path -> dict of float64 arrays with the pathgen names."""
+    if isinstance(src, str):
+        src = dict(np.load(src, allow_pickle=False))
+    need = ('ref_pos', 'ref_vel', 'ref_att', 'ref_accel', 'ref_gyro')
+    alias = {'ref_att': 'ref_att_euler'}
+    out = {}
+    for k in need:
+        key = k if k in src else alias.get(k, k)
+        if key not in src:
+            raise ValueError('trajectory is missing %r' % k)
+        out[k] = np.ascontiguousarray(src[key], dtype=np.float64)
+    n = out['ref_gyro'].shape[0]
+    for k in need:
+        if out[k].shape != (n, 3):
+            raise ValueError('trajectory %s must be (n,3)' % k)
+    if 'time' in src:
+        out['time'] = np.asarray(src['time'], dtype=np.float64)
+    if 'ini' in src:
+        out['ini'] = np.asarray(src['ini'], dtype=np.float64)
+    return out
+
+
+def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetometer=False):
+    """Motion-definition csv/string -> trajectory via the reference's CPU path generator
+    (pathgen.path_gen, pathgen.py:26-329), driven exactly as Sim.__gen_data_from_pathgen
+    does (ins_sim.py:444-472, :578-640)."""
+    try:
+        from gnss_ins_sim.pathgen import pathgen
+    except ImportError:
+        raise RuntimeError(
+            'motion_def is a motion-definition file: generating the true trajectory needs '
+            'gnss_ins_sim.pathgen.path_gen (CPU side, out of scope of this engine). Install '
+            'gnss-ins-sim or pass a precomputed trajectory (dict / .npz) as motion_def.')
+    try:
+        if os.path.isfile(motion_def):
+            ini = np.genfromtxt(motion_def, delimiter=',', skip_header=1, max_rows=1)
+            way = np.genfromtxt(motion_def, delimiter=',', skip_header=3)
+        else:
+            from io import StringIO
+            ini = np.genfromtxt(StringIO(motion_def), delimiter=',', skip_header=1, max_rows=1)
+            way = np.genfromtxt(StringIO(motion_def), delimiter=',', skip_header=3)
+    except Exception:
+        raise ValueError('motion definition file/string must have nine columns '
+                         'and four rows at least (two header rows + at least two data rows).')
+    if way.ndim == 1:
+        way = way.reshape((1, len(way)))
+    ini_pva = ini[:9].astype(np.float64)
+    cmd = way[:, :9].astype(np.float64)
+    ini_pva[0:2] *= D2R
+    ini_pva[6:9] *= D2R
+    cmd[:, 1:4] *= D2R
+    cmd[np.isnan(cmd)] = 0.0
+    if mode is None:
+        mobility = np.array([1.0, 0.5, 2.0])      # 'high_mobility', ins_sim.py:612-640
+    else:
+        mobility = np.array(mode, dtype=np.float64)
+        mobility[1:3] = mobility[1:3] * D2R
+    output_def = np.array([[1.0, fs], [-1.0, fs], [-1.0, fs]])
+    rtn = pathgen.path_gen(ini_pva, cmd, output_def, mobility, ref_frame, magnetometer)
+    return {'time': rtn['nav'][:, 0] / fs, 'ref_pos': np.ascontiguousarray(rtn['nav'][:, 1:4]),
+            'ref_vel': np.ascontiguousarray(rtn['nav'][:, 4:7]),
+            'ref_att': np.ascontiguousarray(rtn['nav'][:, 7:10]),
+            'ref_accel': np.ascontiguousarray(rtn['imu'][:, 1:4]),
+            'ref_gyro': np.ascontiguousarray(rtn['imu'][:, 4:7]), 'ini': ini_pva}
+
+
+class LazyRuns(Mapping):
+    """dict-like {key: (n,3) array} of per-run histories, materialised on first access by
+    re-running the requested runs with history output (deterministic Philox streams)."""
+
+    def __init__(self, sim, name, keys, run_of_key):
+        self._sim, self._name, self._keys, self._run = sim, name, list(keys), dict(run_of_key)
+
+    def __iter__(self):
+        return iter(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+    def __getitem__(self, key):
+        if key not in self._run:
+            raise KeyError(key)
+        return self._sim._history(self._name, self._run[key])
+
+
+# ------------------------------------------------------------------ the facade --
+_UNITS = {  # name -> (description, units, output units)   ins_data_manager.py:85-216
+    'att_euler': ('simulation attitude (Euler, ZYX)  from algo', ['rad'] * 3, ['deg'] * 3),
+    'pos': ('simulation position from algo', ['rad', 'rad', 'm'], ['deg', 'deg', 'm']),
+    'vel': ('simulation velocity from algo', ['m/s'] * 3, ['m/s'] * 3),
+}
+
+
+class Sim(object):
+    '''
+    INS Monte-Carlo simulation engine (device-backed).
+    '''
+
+    def __init__(self, fs, motion_def, ref_frame=0, imu=None, mode=None, env=None,
+                 algorithm=None, seed=0, lanes_per_run=0, history_block=32, run_base=0):
+        '''
+        Args: as gnss_ins_sim.sim.ins_sim.Sim (ins_sim.py:31-124), plus
+            seed: Philox key of the experiment (the reference is unseeded; here every
+                (seed, run) pair names one reproducible noise realisation).
+            lanes_per_run: CUDA lane-group width (0 = automatic).
+            history_block: runs materialised together on a lazy history access.
+            run_base: Philox stream id of run 0 (run r draws stream run_base + r), so that
+                separate experiments can extend one ensemble without reusing streams.
+        '''
+        self.fs = list(fs) if isinstance(fs, (list, tuple, np.ndarray)) else [float(fs), 0.0, 0.0]
+        self.imu = imu
+        self.mode = mode
+        self.env = env
+        self.ref_frame = ref_frame if ref_frame in (0, 1) else 0
+        self.seed = int(seed)
+        self.lanes_per_run = int(lanes_per_run)
+        self.history_block = int(history_block)
+        self.run_base = int(run_base)
+        self.data_src = motion_def
+        self.sim_count = 1
+        self.sim_complete = False
+        self.sim_results = False
+        self.sum = ''
+        self.algo = algorithm
+        if algorithm is not None and not isinstance(algorithm, (list, tuple)):
+            self.algo = [algorithm]
+        if self.algo is not None:
+            for a in self.algo:   # InsAlgoMgr.__check_algo, ins_algo_manager.py:116-127
+                try:
+                    ok = len(a.input) >= 1 and len(a.output) >= 1
+                except Exception:
+                    ok = False
+                if not ok:
+                    raise ValueError('algorithm input or output is not a valid list or tuple.')
+        self.data = {}          # name -> ndarray | dict-of-runs | LazyRuns
+        self.err_stats = {}     # end-point ensemble statistics of the last run()
+        self._traj = None
+        self._dev = None
+        self._cache = {}
+
+    # ---- names ------------------------------------------------------------
+    def algo_name(self, i):
+        """InsAlgoMgr.get_algo_name, ins_algo_manager.py:98-114"""
+        a = self.algo[i]
+        return a.name if hasattr(a, 'name') else 'algo' + str(i)
+
+    # ---- trajectory -------------------------------------------------------
+    def _load_trajectory(self):
+        src = self.data_src
+        if isinstance(src, dict) or (isinstance(src, str) and src.endswith('.npz')):
+            traj = load_trajectory(src)
+        elif isinstance(src, str):
+            if os.path.isdir(src):
+                raise NotImplementedError(
+                    'logged-data directories are read by the reference Sim; feed the arrays to '
+                    'FreeIntegration.run_batch / Allan.run_batch instead')
+            traj = trajectory_from_motion_def(self.fs[0], src, self.ref_frame, self.mode,
+                                              bool(self.imu and self.imu.magnetometer))
+        else:
+            raise TypeError('motion_def must be a trajectory dict, an .npz path or a motion '
+                            'definition csv/string')
+        n = traj['ref_gyro'].shape[0]
+        if 'time' not in traj:
+            traj['time'] = np.arange(n) / self.fs[0]
+        self._traj = traj
+        d = self.data
+        d['fs'], d['ref_frame'], d['time'] = self.fs[0], self.ref_frame, traj['time']
+        d['ref_pos'], d['ref_vel'], d['ref_att_euler'] = traj['ref_pos'], traj['ref_vel'], traj['ref_att']
+        d['ref_accel'], d['ref_gyro'] = traj['ref_accel'], traj['ref_gyro']
+        nav = np.concatenate([traj['ref_att'], traj['ref_pos'], traj['ref_vel']], axis=1)
+        self._dev = {'ref_gyro': engine.to_device(traj['ref_gyro']),
+                     'ref_accel': engine.to_device(traj['ref_accel']),
+                     'ref_nav': engine.to_device(nav)}
+
+    # ---- run ----------------------------------------------------------------
+    def run(self, num_times=1):
+        '''
+        run simulation.
+        Args:
+            num_times: run the simulation for num_times times with given IMU error model.
+        '''
+        self.sim_count = max(int(num_times), 1)
+        if self.imu is None:
+            raise ValueError('imu must be an IMU model when data are generated from a trajectory')
+        if self._traj is None:
+            self._load_trajectory()
+        self._cache = {}
+        self.err_stats = {}
+        self._mc = {}
+        self._vib_acc = parse_env(self.env['acc'], self.fs[0]) if self.env and 'acc' in self.env else None
+        self._vib_gyro = parse_env(self.env['gyro'], self.fs[0]) if self.env and 'gyro' in self.env else None
+        for v in (self._vib_acc, self._vib_gyro):
+            if v is not None and v['type'] == 'psd':
+                raise NotImplementedError('PSD vibration is not built yet (K5)')
+        R = self.sim_count
+        self._shard = dist.shard(R)
+        keys = list(range(R))
+        self.data['accel'] = LazyRuns(self, 'accel', keys, {k: k for k in keys})
+        self.data['gyro'] = LazyRuns(self, 'gyro', keys, {k: k for k in keys})
+        if self.algo is not None:
+            for i, a in enumerate(self.algo):
+                if isinstance(a, FreeIntegration):
+                    self._run_free_integration(i, a)
+                elif isinstance(a, Allan):
+                    self._run_allan(i, a)
+                else:
+                    self._run_foreign(i, a)
+        self.sim_complete = True
+
+    def _mc_config(self, ai, runs, r0, stats_start=-1, dump_runs=0):
+        """Config for experiment runs [r0, r0+runs) of algorithm ai.  Philox streams are
+        named by the experiment run index (all algorithms see the same sensor data, as in
+        the reference where loop A runs once); the initial-state rule counts the plugin's
+        own run_times."""
+        algo = self.algo[ai]
+        n = self._traj['ref_gyro'].shape[0]
+        return engine.make_mc_config(
+            self.ref_frame, self.fs[0], n, runs, self.seed, self.imu.gyro_err, self.imu.accel_err,
+            algo.ini_sets.shape[0], algo.ini_sets.shape[1], earth_rot=algo.earth_rot,
+            run_offset=self.run_base + r0, ini_offset=self._mc[ai]['base'] + r0,
+            vib_gyro=self._vib_gyro, vib_accel=self._vib_acc,
+            lanes_per_run=self.lanes_per_run or algo.lanes_per_run, stats_start=stats_start,
+            dump_runs=dump_runs)
+
+    def _run_free_integration(self, i, algo):
+        name = self.algo_name(i)
+        lo, hi = self._shard
+        d = self._dev
+        self._mc[i] = {'base': algo.run_times, 'res': None}   # plugin's run counter at run 0
+        res = None
+        if hi > lo:
+            cfg = self._mc_config(i, hi - lo, lo)
+            res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
+                                             algo.ini_device(), want_state=True)
+        algo.run_times += self.sim_count
+        self._mc[i]['res'] = res
+        self.err_stats[name] = dist.ensemble_stats(res.end_err if res is not None else None,
+                                                   self.sim_count)
+        keys = ['%s_%d' % (name, k) for k in range(self.sim_count)]
+        run_of = {k: r for r, k in enumerate(keys)}
+        for out in ('att_euler', 'pos', 'vel'):
+            prev = self.data.get(out)
+            lazy = LazyRuns(self, (i, out), keys, run_of)
+            if isinstance(prev, _Merged):
+                prev.add(lazy)
+            elif isinstance(prev, LazyRuns) and prev._name[0] != i:
+                self.data[out] = _Merged([prev, lazy])
+            else:
+                self.data[out] = lazy
+
+    def _noise_block(self, r0, r1):
+        """K1 for global-in-experiment runs [r0, r1): CUDA gyro, accel [r1-r0, n, 3]."""
+        d = self._dev
+        return engine.imu_noise(self.fs[0], r1 - r0, d['ref_gyro'], d['ref_accel'],
+                                self.imu.gyro_err, self.imu.accel_err, self.seed,
+                                run_offset=self.run_base + r0, vib_gyro=self._vib_gyro,
+                                vib_accel=self._vib_acc)
+
+    def _run_allan(self, i, algo):
+        name = self.algo_name(i)
+        R = self.sim_count
+        n = self._traj['ref_gyro'].shape[0]
+        block = max(1, min(R, int(2e9 // (n * 48)) or 1))
+        tau_all, ada, adg = None, {}, {}
+        for r0 in range(0, R, block):
+            r1 = min(R, r0 + block)
+            gyro, accel = self._noise_block(r0, r1)
+            tau, a, g = algo.run_batch(self.fs[0], accel, gyro)
+            for r in range(r0, r1):
+                ada['%s_%d' % (name, r)] = a[r - r0]
+                adg['%s_%d' % (name, r)] = g[r - r0]
+            tau_all = tau
+        self.data['algo_time'] = {'%s_%d' % (name, r): tau_all for r in range(R)}
+        self.data['ad_accel'] = ada
+        self.data['ad_gyro'] = adg
+
+    def _run_foreign(self, i, algo):
+        """Reference-style plugin run on the host, sensor data from K1
+        (the per-run protocol of InsAlgoMgr.run_algo, ins_algo_manager.py:73-95)."""
+        import copy
+        name = self.algo_name(i)
+        outs = {o: {} for o in algo.output}
+        static = {'fs': self.fs[0], 'ref_frame': self.ref_frame, 'time': self.data['time']}
+        for r in range(self.sim_count):
+            gyro, accel = self._noise_block(r, r + 1)
+            per_run = {'gyro': gyro[0].cpu().numpy(), 'accel': accel[0].cpu().numpy()}
+            args = []
+            for nm in algo.input:
+                if nm in per_run:
+                    args.append(per_run[nm])
+                elif nm in static:
+                    args.append(static[nm])
+                elif nm in self.data and not isinstance(self.data[nm], (dict, Mapping)):
+                    args.append(self.data[nm])
+                else:
+                    raise ValueError('algorithm input %r is not generated by this engine' % nm)
+            algo.reset()
+            algo.run(copy.deepcopy(args))
+            res = algo.get_results()
+            for o, v in zip(algo.output, res):
+                outs[o]['%s_%d' % (name, r)] = v
+        for o in algo.output:
+            self.data[o] = outs[o]
+
+    # ---- lazy histories -------------------------------------------------------
+    def _history(self, name, run):
+        """(n,3) history of one run; materialises a block of neighbouring runs at once."""
+        blk = run // self.history_block
+        if isinstance(name, tuple):      # algorithm output (algo index, data name)
+            ai, out = name
+            key = ('nav', ai, blk)
+            if key not in self._cache:
+                algo = self.algo[ai]
+                r0 = blk * self.history_block
+                r1 = min(self.sim_count, r0 + self.history_block)
+                cfg = self._mc_config(ai, r1 - r0, r0, dump_runs=r1 - r0)
+                d = self._dev
+                res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
+                                                 algo.ini_device(), dump_nav=True, dump_imu=True)
+                self._cache[key] = {'att_euler': res.att.cpu().numpy(), 'pos': res.pos.cpu().numpy(),
+                                    'vel': res.vel.cpu().numpy()}
+                self._cache[('imu', blk)] = {'gyro': res.gyro.cpu().numpy(),
+                                             'accel': res.accel.cpu().numpy()}
+            return self._cache[key][out][run - blk * self.history_block]
+        key = ('imu', blk)
+        if key not in self._cache:
+            r0 = blk * self.history_block
+            r1 = min(self.sim_count, r0 + self.history_block)
+            gyro, accel = self._noise_block(r0, r1)
+            self._cache[key] = {'gyro': gyro.cpu().numpy(), 'accel': accel.cpu().numpy()}
+        return self._cache[key][name][run - blk * self.history_block]
+
+    # ---- results --------------------------------------------------------------
+    def get_names_of_available_data(self):
+        return list(self.data.keys())
+
+    def get_data(self, data_names):
+        '''
+        Get data by names (ins_sim.py:317-327): list of arrays / dicts of runs.
+        '''
+        return [self.data[n] if n in self.data else None for n in data_names]
+
+    def end_point_errors(self, algo_index=0):
+        '''
+        [R_local, 9] end-point errors (att wrapped [rad], pos, vel) of this rank's runs, as a
+        CUDA tensor -- 72 bytes per run, the raw material of the ensemble statistics.
+        '''
+        res = self._mc[algo_index]['res']
+        return res.end_err if res is not None else None
+
+    def get_error_stats(self, data_name, err_stats_start=-1, angle=False, use_output_units=False,
+                        extra_opt='', algo_index=0):
+        '''
+        InsDataMgr.get_error_stats (ins_data_manager.py:385-452) for att_euler / pos / vel.
+        err_stats_start == -1: end-point statistics over runs {'max','avg','std'} (3,).
+        otherwise: per-run process statistics from that time [s]: dicts keyed by run key.
+        '''
+        if data_name not in _UNITS:
+            raise ValueError('error statistics exist for att_euler, pos and vel')
+        c0 = {'att_euler': 0, 'pos': 3, 'vel': 6}[data_name]
+        desc, units, out_units = _UNITS[data_name]
+        if data_name == 'pos' and self.ref_frame == 1:
+            units, out_units = ['m'] * 3, ['m'] * 3
+        name = self.algo_name(algo_index)
+        if err_stats_start == -1:
+            if data_name == 'pos' and self.ref_frame == 0 and extra_opt in ('ned', 'ecef'):
+                st = self._end_point_pos_stats(extra_opt, algo_index)
+                units = out_units = ['m'] * 3
+            else:
+                s = self.err_stats[name]
+                st = {'max': s[0, c0:c0 + 3].copy(), 'avg': s[1, c0:c0 + 3].copy(),
+                      'std': s[2, c0:c0 + 3].copy()}
+        else:
+            st = self._process_stats(algo_index, err_stats_start, c0)
+        if use_output_units:
+            scale = np.array([R2D if (u == 'rad' and o == 'deg') else 1.0
+                              for u, o in zip(units, out_units)])
+            for k in ('max', 'avg', 'std'):
+                if isinstance(st[k], dict):
+                    st[k] = {r: v * scale for r, v in st[k].items()}
+                else:
+                    st[k] = st[k] * scale
+            st['units'] = str(out_units)
+        else:
+            st['units'] = str(units)
+        return st
+
+    def _end_point_pos_stats(self, opt, algo_index):
+        """'ned' / 'ecef' position error of LLA results, ins_data_manager.py:543-552."""
+        res = self._mc[algo_index]['res']
+        state = dist.gather_rows(res.end_state if res is not None else None, self.sim_count)
+        x = state[:, 3:6]
+        r = self._traj['ref_pos'][-1]
+        err = lla2ecef(x) - lla2ecef(r)[0]
+        if opt == 'ned':
+            err = err.dot(ecef_to_ned(r[0], r[1]).T)
+        return {'max': np.max(np.abs(err), 0), 'avg': np.average(err, 0), 'std': np.std(err, 0)}
+
+    def _process_stats(self, algo_index, start_s, c0):
+        key = ('proc', algo_index, float(start_s))
+        if key not in self._cache:
+            t = self.data['time']
+            idx = np.where(t >= start_s)[0]
+            if idx.shape[0] == 0:
+                print('err_stats_start exceeds max data points.')
+                start = 0
+            else:
+                start = int(idx[0])
+            algo = self.algo[algo_index]
+            lo, hi = self._shard
+            d = self._dev
+            ps = None
+            if hi > lo:
+                cfg = self._mc_config(algo_index, hi - lo, lo, stats_start=start)
+                ps = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
+                                                algo.ini_device()).proc_stats.reshape(hi - lo, 27)
+            self._cache[key] = dist.gather_rows(ps, self.sim_count).reshape(-1, 3, 9)
+        ps = self._cache[key]
+        name = self.algo_name(algo_index)
+        out = {'max': {}, 'avg': {}, 'std': {}}
+        for r in range(self.sim_count):
+            k = '%s_%d' % (name, r)
+            out['max'][k] = ps[r, 0, c0:c0 + 3].copy()
+            out['avg'][k] = ps[r, 1, c0:c0 + 3].copy()
+            out['std'][k] = ps[r, 2, c0:c0 + 3].copy()
+        return out
+
+    def results(self, data_dir=None, err_stats_start=0, gen_kml=False, extra_opt=''):
+        '''
+        Simulation summary (ins_sim.py:194-251, :339-413): the configuration and the error
+        statistics of att_euler / pos / vel in output units.  Returns the available data
+        names.  Saving every run to .csv / .kml is the reference's file export (out of
+        scope); data_dir saves summary.txt and the per-run end-point errors only.
+        '''
+        if not self.sim_complete:
+            print("Call Sim.run() to run the simulaltion first.")
+            return None
+        if gen_kml:
+            raise NotImplementedError('kml export is the reference\'s kml_gen (out of scope)')
+        s = '\n------------------------------------------------------------\n'
+        s += 'Sample frequency of IMU: [fs] = %s Hz\n' % str(self.fs[0])
+        s += 'Reference frame: %s\n' % str(self.ref_frame)
+        s += 'Simulation time duration: %s s\n' % str(len(self.data['time']) / self.fs[0])
+        s += 'Simulation runs: %s\n' % str(self.sim_count)
+        has_mc = bool(getattr(self, '_mc', None))
+        if has_mc:
+            s += '\n------------------------------------------------------------\n'
+            s += 'The following are error statistics.'
+            ai = sorted(self._mc.keys())[0]
+            for dn in ('att_euler', 'pos', 'vel'):
+                st = self.get_error_stats(dn, err_stats_start=err_stats_start,
+                                          angle=(dn == 'att_euler'), use_output_units=True,
+                                          extra_opt=extra_opt, algo_index=ai)
+                s += '\n-----------statistics for %s (in units of %s)\n' % (_UNITS[dn][0], st['units'])
+                if isinstance(st['max'], dict):
+                    for run in sorted(st['max'].keys()):
+                        s += '\tSimulation run %s:\n' % str(run)
+                        s += '\t\t--Max error: %s\n' % str(st['max'][run])
+                        s += '\t\t--Avg error: %s\n' % str(st['avg'][run])
+                        s += '\t\t--Std of error: %s\n' % str(st['std'][run])
+                else:
+                    s += '\t--Max error: %s\n' % str(st['max'])
+                    s += '\t--Avg error: %s\n' % str(st['avg'])
+                    s += '\t--Std of error: %s\n' % str(st['std'])
+        self.sum += s
+        if dist.rank() == 0:
+            print(self.sum)
+            if data_dir is not None:
+                os.makedirs(data_dir, exist_ok=True)
+                with open(os.path.join(data_dir, 'summary.txt'), 'w') as f:
+                    f.write(self.sum + '\n')
+        self.sim_results = True
+        return self.get_names_of_available_data()
+
+    def plot(self, what_to_plot, sim_idx=None, opt=None, extra_opt=''):
+        raise NotImplementedError('plotting is the reference\'s sim_data_plot (matplotlib), out '
+                                  'of scope: use get_data() and plot the arrays')
+
+
+class _Merged(Mapping):
+    """Several algorithms writing the same output name: one dict view over all of them."""
+
+    def __init__(self, parts):
+        self._parts = list(parts)
+
+    def add(self, p):
+        self._parts.append(p)
+
+    def __iter__(self):
+        for p in self._parts:
+            yield from p
+
+    def __len__(self):
+        return sum(len(p) for p in self._parts)
+
+    def __getitem__(self, key):
+        for p in self._parts:
+            if key in p._run:
+                return p[key]
+        raise KeyError(key)

@@ -1,0 +1,204 @@
+/*
+ * b2ins -- B200-native Monte-Carlo strapdown-INS engine: C ABI.
+ *
+ * This is the drop-in boundary for the Monte-Carlo free-integration hot path of
+ * gnss-ins-sim.  Every entry point names the reference
+ * interface it replaces (file:line relative to the gnss-ins-sim checkout).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all floating point is IEEE double ("f64").
+ *   - functions return B2INS_OK (0) or an error code; b2ins_last_error() gives text
+ *     (thread-local).  Nothing is allocated across the boundary: the caller owns
+ *     every buffer.
+ *   - entry points WITHOUT a suffix take DEVICE pointers and a CUDA stream
+ *     (void* = cudaStream_t, NULL = legacy default stream) and are asynchronous.
+ *   - entry points ending in _host take HOST pointers, do the H2D / D2H copies
+ *     themselves on an internal stream and return when the results are in the
+ *     caller's buffers (this is what a ctypes / cgo / JNI stub binds first).
+ *   - series of per-run 3-vectors x(run r, sample t, component c) use one of two
+ *     layouts:
+ *       B2INS_LAYOUT_RUN_MAJOR  [R][n][3]  -- run r is exactly the reference's
+ *                                             (n,3) C-contiguous numpy array
+ *       B2INS_LAYOUT_TIME_MAJOR [n][3][R]  -- device-native for lanes_per_run = 1
+ *   - "ini" is [ini_sets][ini_rows] (ini_rows = 9: lat,lon,alt [rad,rad,m], body
+ *     velocity [m/s], yaw,pitch,roll [rad]; ini_rows = 10 adds a gravity override
+ *     [m/s^2]) -- the transpose of FreeIntegration's ini_pos_vel_att
+ *     (free_integration.py:19-61).  Global run g uses set g if g < ini_sets,
+ *     else set 0 (free_integration.py:85-87).
+ */
+#ifndef B2INS_H_
+#define B2INS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2INS_VERSION 100 /* 0.1.0 */
+
+#define B2INS_OK 0
+#define B2INS_ERR_ARG 1    /* bad argument (NULL, size, alignment, enum) */
+#define B2INS_ERR_CUDA 2   /* a CUDA call or kernel failed */
+#define B2INS_ERR_NODEV 3  /* no usable CUDA device */
+
+#define B2INS_LAYOUT_RUN_MAJOR 0
+#define B2INS_LAYOUT_TIME_MAJOR 1
+
+#define B2INS_VIB_NONE 0
+#define B2INS_VIB_RANDOM 1     /* pathgen.py:486-489 / :549-552 */
+#define B2INS_VIB_SINUSOIDAL 2 /* pathgen.py:490-493 / :553-555 (gyro: random phase) */
+#define B2INS_VIB_SERIES 3     /* precomputed per-axis series (PSD model), see b2ins_psd_series_f64 */
+
+/* Sensor error model of one triad: pathgen.acc_gen / gyro_gen `acc_err` / `gyro_err`
+ * dicts (pathgen.py:441-466, :503-528), already in SI units as produced by
+ * imu_model.IMU (imu_model.py:138-143). */
+typedef struct b2ins_sensor_err {
+  double b[3];       /* constant bias */
+  double b_drift[3]; /* bias-instability 1-sigma */
+  double b_corr[3];  /* Gauss-Markov correlation time [s]; +inf => white drift (pathgen.py:591-593) */
+  double rw[3];      /* 'arw' [rad/s/sqrt(Hz)] or 'vrw' [m/s^2/sqrt(Hz)] */
+} b2ins_sensor_err;
+
+/* Vibration model of one triad: Sim.__parse_env output (ins_sim.py:642-701). */
+typedef struct b2ins_vib {
+  int32_t type; /* B2INS_VIB_* */
+  int32_t series_len; /* VIB_SERIES: period of the series (<= 16384, it is tiled to n like
+                         time_series_from_psd.py:59-62) */
+  double amp[3];  /* RANDOM: 1-sigma; SINUSOIDAL: amplitude */
+  double freq;    /* SINUSOIDAL: Hz */
+  const double* series; /* VIB_SERIES: device pointer [runs][3][series_len], else NULL */
+} b2ins_vib;
+
+/* One Monte-Carlo experiment: loops A and B of Sim.run (ins_sim.py:490-506,
+ * ins_algo_manager.py:73-95) for `runs` runs starting at global run id `run_offset`. */
+typedef struct b2ins_mc_config {
+  int32_t ref_frame;  /* 0 NED/LLA, 1 virtual inertial (free_integration.py:83,117) */
+  int32_t earth_rot;  /* FreeIntegration(earth_rot=...), only used when ref_frame == 0 */
+  double fs;          /* IMU sample rate [Hz] */
+  int64_t n;          /* samples per run */
+  int64_t runs;       /* runs computed by this call (this rank's shard) */
+  int64_t run_offset; /* global id of local run 0: names the Philox stream of every run */
+  int64_t ini_offset; /* local run r is simulation run ini_offset + r for the initial-state rule
+                         (FreeIntegration.run_times, free_integration.py:85-87) */
+  uint64_t seed;      /* Philox key */
+  b2ins_sensor_err gyro_err;
+  b2ins_sensor_err accel_err;
+  b2ins_vib vib_gyro;
+  b2ins_vib vib_accel;
+  int32_t ini_sets;
+  int32_t ini_rows;       /* 9 or 10 */
+  int32_t lanes_per_run;  /* 0 = choose from runs; else 1,2,4,8,16,32 (32 = one warp owns one run) */
+  int32_t stats_start;    /* first sample index of the per-run process-error statistics
+                             (ins_data_manager.py:761-795); < 0 = end-point errors only */
+  int64_t dump_runs;      /* full histories are written for local runs [0, dump_runs) */
+} b2ins_mc_config;
+
+/* ---- housekeeping ------------------------------------------------------ */
+int b2ins_version(void);
+const char* b2ins_last_error(void);
+int b2ins_device_count(void);
+/* number of Allan cluster sizes allan.allan_var produces for (n, fs), allan.py:29-44;
+ * fills m[0..] (may be NULL) -- host helper, no GPU */
+int b2ins_allan_num_tau(int64_t n, double fs, int64_t* m, int m_cap);
+
+/* ---- K2: strapdown free integration, noise supplied ---------------------
+ * Replaces FreeIntegration.run + get_results (demo_algorithms/free_integration.py:63-180)
+ * and the per-run dispatch loop InsAlgoMgr.run_algo (ins_algo_manager.py:73-95).
+ * gyro [rad/s], accel [m/s^2]: `layout`; att [yaw,pitch,roll rad], pos (LLA rad,rad,m if
+ * ref_frame 0, ECEF-offset xyz m if ref_frame 1), vel (NED m/s): same layout. */
+int b2ins_free_integration_f64(int ref_frame, double fs, int64_t runs, int64_t n,
+                               const double* gyro, const double* accel, int layout,
+                               const double* ini, int ini_sets, int ini_rows,
+                               int64_t run_offset, int earth_rot,
+                               double* att, double* pos, double* vel,
+                               int lanes_per_run, void* stream);
+int b2ins_free_integration_f64_host(int ref_frame, double fs, int64_t runs, int64_t n,
+                                    const double* gyro, const double* accel, int layout,
+                                    const double* ini, int ini_sets, int ini_rows,
+                                    int64_t run_offset, int earth_rot,
+                                    double* att, double* pos, double* vel, int lanes_per_run);
+
+/* ---- K1: IMU sensor-error generator --------------------------------------
+ * Replaces pathgen.acc_gen / gyro_gen / bias_drift (pathgen.py:441-594) for `runs` runs:
+ * meas = ref + b + drift + white + vib with on-device Philox4x32-10 normals keyed by
+ * (seed, run_offset + r).  ref_gyro / ref_accel: [n][3] shared true IMU output.
+ * gyro / accel: outputs in `layout`.  z_dump (nullable): the 12 normals per (run, t) as
+ * [R][n][12] = (acc_gm[3], acc_w[3], gyr_gm[3], gyr_w[3]) for injection into the
+ * reference's np.random.randn call sequence. */
+int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n,
+                        const double* ref_gyro, const double* ref_accel,
+                        const b2ins_sensor_err* gyro_err, const b2ins_sensor_err* accel_err,
+                        const b2ins_vib* vib_gyro, const b2ins_vib* vib_accel,
+                        uint64_t seed, int64_t run_offset, int layout,
+                        double* gyro, double* accel, double* z_dump, void* stream);
+int b2ins_imu_noise_f64_host(double fs, int64_t runs, int64_t n,
+                             const double* ref_gyro, const double* ref_accel,
+                             const b2ins_sensor_err* gyro_err, const b2ins_sensor_err* accel_err,
+                             const b2ins_vib* vib_gyro, const b2ins_vib* vib_accel,
+                             uint64_t seed, int64_t run_offset, int layout,
+                             double* gyro, double* accel, double* z_dump);
+
+/* ---- K12: fused Monte-Carlo run (noise -> integration -> per-run errors) --
+ * Replaces loop A (ins_sim.py:490-496) + loop B (ins_algo_manager.py:73-95) + the per-run
+ * part of InsDataMgr.calc_data_err / array_error (ins_data_manager.py:454-541).
+ *   ref_gyro, ref_accel [n][3]: true IMU output (pathgen.path_gen 'imu').
+ *   ref_nav [n][9]: true att(yaw,pitch,roll), pos, vel per sample (pathgen 'nav',
+ *            reordered).  Only row n-1 is read unless cfg->stats_start >= 0.
+ *   ini [ini_sets][ini_rows].
+ *   end_err [runs][9]: (att wrapped to [-pi,pi], pos, vel) error at sample n-1.
+ *   end_state [runs][9] (nullable): att, pos, vel at sample n-1.
+ *   proc_stats [runs][3][9] (nullable unless stats_start >= 0): per-run max|e|, mean, std
+ *            (ddof 0) of the error over samples >= stats_start.
+ *   dump_att/pos/vel, dump_gyro/accel (each nullable): [dump_runs][n][3] histories.
+ * Asynchronous on `stream`. */
+int b2ins_mc_free_integration_f64(const b2ins_mc_config* cfg,
+                                  const double* ref_gyro, const double* ref_accel,
+                                  const double* ref_nav, const double* ini,
+                                  double* end_err, double* end_state, double* proc_stats,
+                                  double* dump_att, double* dump_pos, double* dump_vel,
+                                  double* dump_gyro, double* dump_accel, void* stream);
+/* Host-buffer convenience: copies ref/ini up, runs K12 + K3, copies end_err [runs][9] and
+ * stats [3][9] back.  end_err may be NULL (stats only). */
+int b2ins_mc_free_integration_f64_host(const b2ins_mc_config* cfg,
+                                       const double* ref_gyro, const double* ref_accel,
+                                       const double* ref_nav, const double* ini,
+                                       double* end_err, double* stats);
+
+/* ---- K3: ensemble error statistics ---------------------------------------
+ * Replaces InsDataMgr.__end_point_error_stats / __array_stats
+ * (ins_data_manager.py:717-759, :797-808) on a [runs][ncomp] error matrix.
+ * Two-phase so that a multi-GPU caller can all-reduce in between:
+ *   phase 1: partial[0..ncomp) = sum e, partial[ncomp..2ncomp) = max|e|  (this shard)
+ *   (caller all-reduces: SUM the first ncomp, MAX the second ncomp, and the run count)
+ *   phase 2: given mean[ncomp], partial2[0..ncomp) = sum (e-mean)^2
+ * b2ins_error_stats_f64 does both phases for a single shard and writes
+ * stats [3][ncomp] = max|e|, mean, std(ddof 0).  ncomp <= 32.  All reductions are
+ * deterministic (fixed order, no floating-point atomics).  workspace: device scratch of
+ * b2ins_error_stats_workspace_bytes(ncomp) bytes. */
+int64_t b2ins_error_stats_workspace_bytes(int ncomp);
+int b2ins_error_partial_f64(int64_t runs, int ncomp, const double* err, double* partial,
+                            void* workspace, void* stream);
+int b2ins_error_partial2_f64(int64_t runs, int ncomp, const double* err, const double* mean,
+                             double* partial2, void* workspace, void* stream);
+int b2ins_error_stats_f64(int64_t runs, int ncomp, const double* err, double* stats,
+                          void* workspace, void* stream);
+
+/* ---- K4: Allan variance ---------------------------------------------------
+ * Replaces allan.allan_var (allan/allan.py:18-59) for `nseries` series at once.
+ * Series s, sample t lives at x[s / inner * outer_stride + (s % inner) + t * sample_stride]
+ * (RUN_MAJOR accel [R][n][3]: inner = 3, outer_stride = 3n, sample_stride = 3).
+ * avar [nseries][ntau], tau [ntau], ntau = b2ins_allan_num_tau(n, fs).
+ * workspace: device scratch of b2ins_allan_workspace_bytes(n, nseries) bytes. */
+int64_t b2ins_allan_workspace_bytes(int64_t n, int64_t nseries);
+int b2ins_allan_f64(double fs, int64_t n, int64_t nseries, const double* x,
+                    int64_t inner, int64_t outer_stride, int64_t sample_stride,
+                    double* avar, double* tau, void* workspace, void* stream);
+int b2ins_allan_f64_host(double fs, int64_t n, int64_t nseries, const double* x,
+                         int64_t inner, int64_t outer_stride, int64_t sample_stride,
+                         double* avar, double* tau);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2INS_H_ */

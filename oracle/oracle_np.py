@@ -210,8 +210,8 @@ _S32 = np.uint64(32)
 PAIR_ACCEL = 0      # +axis : (GM drive, white) of accel axis
 PAIR_GYRO = 3       # +axis : (GM drive, white) of gyro axis
 PAIR_VIB = 6        # +axis : (accel random vib, gyro random vib)
-PAIR_PHASE = 9      # t = 0xFFFFFFFF : sinusoidal gyro vib phases / psd blocks start at 16
-PAIR_PSD = 16       # +6*? see psd_phase_normals
+PAIR_PHASE = 9      # +axis, t = 0xFFFFFFFF : sinusoidal gyro-vib phase uniforms
+PAIR_PSD = 16       # +3*sensor+axis (sensor 0 accel, 1 gyro), t = bin index: PSD phases (z0)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -239,7 +239,8 @@ def normal_pair(t, pair, run, seed):
     """Two independent N(0,1) float64 for (run, t, pair) under `seed`.
 
     counter = (t, pair, run_lo, run_hi), key = (seed_lo, seed_hi).
-    u1 = ((x1:x0 >> 11) + 1) * 2^-53 in (0, 1],  u2 = (x3:x2 >> 11) * 2^-53 in [0, 1).
+    u1 = 1 - (x1:x0 >> 12) * 2^-52 in (0, 1],  u2 = (x3:x2 >> 12) * 2^-52 in [0, 1)
+    (both exact in float64; the device builds them from the bit pattern).
     r = sqrt(-2 ln u1);  z0 = r cos(2 pi u2), z1 = r sin(2 pi u2).
     """
     run = np.asarray(run, dtype=np.uint64)
@@ -248,8 +249,8 @@ def normal_pair(t, pair, run, seed):
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     a = (x1 << _S32) | x0
     b = (x3 << _S32) | x2
-    u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) * (2.0 ** -53)
-    u2 = (b >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
+    u1 = 1.0 - (a >> np.uint64(12)).astype(np.float64) * (2.0 ** -52)
+    u2 = (b >> np.uint64(12)).astype(np.float64) * (2.0 ** -52)
     r = np.sqrt(-2.0 * np.log(u1))
     th = TWO_PI * u2
     return r * np.cos(th), r * np.sin(th)
@@ -284,7 +285,7 @@ def gyro_vib_phase_uniforms(run_ids, seed):
     x0, x1, _, _ = philox4x32_10(0xFFFFFFFF, PAIR_PHASE + ax, r & _MASK, r >> _S32,
                                  seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     a = (x1 << _S32) | x0
-    return (a >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
+    return (a >> np.uint64(12)).astype(np.float64) * (2.0 ** -52)
 
 
 def gm_coeffs(corr, drift, fs):
