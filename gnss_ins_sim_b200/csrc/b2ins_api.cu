@@ -578,4 +578,40 @@ int b2ins_allan_f64_host(double fs, int64_t n, int64_t nseries, const double* x,
   return B2INS_OK;
 }
 
+// ---------------------------------------------------------------- diag ------
+__global__ void dfma_rate_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
+         a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int b2ins_diag_dfma_rate(double* dfma_per_s) {
+  ARG_CHECK(dfma_per_s, "null output");
+  const int blocks = sm_count() * 8, threads = 256, iters = 8000;
+  DevBuf out;
+  CU_CHECK(out.alloc(sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CU_CHECK(cudaEventCreate(&e0));
+  CU_CHECK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+    CU_CHECK(cudaEventRecord(e0, nullptr));
+    dfma_rate_kernel<<<blocks, threads>>>(out.d(), iters);
+    CU_CHECK(cudaEventRecord(e1, nullptr));
+    CU_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *dfma_per_s = static_cast<double>(blocks) * threads * iters * 8.0 / (best * 1e-3);
+  return B2INS_OK;
+}
+
 }  // extern "C"

@@ -34,7 +34,8 @@ def to_device(a, device=None):
     if isinstance(a, torch.Tensor):
         return a.to(device=device or 'cuda', dtype=torch.float64).contiguous()
     a = np.ascontiguousarray(a, dtype=np.float64)
-    return torch.from_numpy(a).to(device or 'cuda')
+    t = torch.from_numpy(a)
+    return t.to(device or 'cuda', non_blocking=t.is_pinned())
 
 
 def ini_sets_from_plugin(ini_pos_vel_att):

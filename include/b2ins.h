@@ -198,6 +198,13 @@ int b2ins_allan_f64_host(double fs, int64_t n, int64_t nseries, const double* x,
                          int64_t inner, int64_t outer_stride, int64_t sample_stride,
                          double* avar, double* tau);
 
+/* ---- diagnostics ---------------------------------------------------------
+ * Measured FP64 FMA issue rate of the current device [lane-FMA/s]: a ~10 ms dependent-chain
+ * microbenchmark (8 independent chains per thread, every SM filled).  The Monte-Carlo
+ * kernels are FP64-instruction-bound, so this is the denominator bench.py reports their
+ * FP64 utilisation against (beside the HBM roofline).  Synchronous. */
+int b2ins_diag_dfma_rate(double* dfma_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,156 @@
+"""GPU tests of the host-side mirror of the reference interface: the FreeIntegration / Allan
+plugins through the reference's plugin protocol and the Sim facade, against the reference's
+golden vectors."""
+import numpy as np
+import pytest
+
+import oracle_np as onp
+from conftest import load_golden, assert_close, wrap_pi
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+@pytest.fixture(scope='module')
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return True
+
+
+def _traj(g):
+    return {k: g[k] for k in ('time', 'ref_pos', 'ref_vel', 'ref_att', 'ref_accel', 'ref_gyro')}
+
+
+def test_plugin_protocol_like_insalgomgr(gpu):
+    """reset() -> run(set_of_input) -> get_results() per run, ins_algo_manager.py:77-95."""
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    for rf in (1, 0):
+        g = load_golden('seeded_90deg_rf%d.npz' % rf)
+        algo = FreeIntegration(g['ini'])
+        for r in range(2):
+            algo.reset()
+            algo.run([rf, 100.0, g['gyro'][r].copy(), g['accel'][r].copy()])
+            att, pos, vel = algo.get_results()
+            assert att.shape == (1000, 3)
+            assert np.abs(wrap_pi(att - g['att'][r])).max() < 1e-9
+            assert_close(pos, g['pos'][r], 1e-9, 1.0, 'pos')
+            assert_close(vel, g['vel'][r], 1e-9, 1.0, 'vel')
+        assert algo.run_times == 2
+    # run k uses initial-state set k-1 while k <= sets, then set 0 (free_integration.py:85-87)
+    g = load_golden('seeded_90deg_rf1.npz')
+    inis = np.tile(g['ini'][:, None], (1, 2))
+    inis[3, 1] += 0.5
+    algo = FreeIntegration(inis)
+    outs = []
+    for r in range(3):
+        algo.run([1, 100.0, g['gyro'][0], g['accel'][0]])
+        outs.append(algo.get_results()[2][0].copy())
+    assert not np.allclose(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize('rf', [1, 0])
+def test_sim_facade_matches_reference_summary(gpu, rf, capsys):
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    g = load_golden('philox_90deg_mid_rf%d.npz' % rf)
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=False)
+    sim = Sim([100.0, 0.0, 0.0], _traj(g), ref_frame=rf, imu=imu,
+              algorithm=FreeIntegration(g['ini']), seed=int(g['seed']))
+    sim.run(8)
+    names = sim.results(err_stats_start=-1)
+    out = capsys.readouterr().out
+    assert 'Simulation runs: 8' in out and 'Reference frame: %d' % rf in out
+    assert 'statistics for simulation position from algo' in out
+    for n in ('att_euler', 'pos', 'vel', 'accel', 'gyro', 'ref_pos', 'time'):
+        assert n in names
+    for dn, key in (('att_euler', 'att_euler'), ('pos', 'pos'), ('vel', 'vel')):
+        st = sim.get_error_stats(dn, err_stats_start=-1, angle=(dn == 'att_euler'))
+        for k in ('max', 'avg', 'std'):
+            assert_close(st[k], g['stat_%s_%s' % (key, k)], 1e-6, 1e-3, '%s %s' % (dn, k))
+    # output units: deg for angles (and for lat/lon when ref_frame == 0)
+    st = sim.get_error_stats('att_euler', -1, angle=True, use_output_units=True)
+    assert_close(st['std'], g['stat_att_euler_std'] * 180 / np.pi, 1e-6, 1e-3, 'deg')
+    assert st['units'] == "['deg', 'deg', 'deg']"
+    # lazily materialised histories use the reference's keys
+    pos = sim.get_data(['pos'])[0]
+    assert list(pos.keys())[:2] == ['algo0_0', 'algo0_1'] and len(pos) == 8
+    assert_close(pos['algo0_3'], g['pos'][3], 1e-9, 1.0, 'pos history')
+    att = sim.get_data(['att_euler'])[0]['algo0_7']
+    assert np.abs(wrap_pi(att - g['att'][7])).max() < 1e-8
+    gyro = sim.get_data(['gyro'])[0]
+    assert_close(gyro[5], g['gyro'][5], 1e-12, 1.0, 'gyro history')
+    assert_close(sim.get_data(['accel'])[0][0], g['accel'][0], 1e-12, 1.0, 'accel history')
+    # per-run process statistics from t >= 2.5 s (ins_data_manager.py:761-795)
+    ps = sim.get_error_stats('vel', err_stats_start=2.5)
+    o = onp.process_error_stats(g['vel'], g['ref_vel'], 250)
+    for k in ('max', 'avg', 'std'):
+        got = np.stack([ps[k]['algo0_%d' % r] for r in range(8)])
+        assert_close(got, o[k], 1e-6, 1e-4, 'proc ' + k)
+    if rf == 0:   # 'ned' option: LLA error -> metres in the local NED frame (:543-552)
+        from gnss_ins_sim_b200.sim import lla2ecef, ecef_to_ned
+        st = sim.get_error_stats('pos', -1, extra_opt='ned')
+        e = lla2ecef(g['pos'][:, -1]) - lla2ecef(g['ref_pos'][-1])[0]
+        e = e.dot(ecef_to_ned(g['ref_pos'][-1, 0], g['ref_pos'][-1, 1]).T)
+        assert_close(st['std'], e.std(0), 1e-6, 1e-3, 'ned std')
+        assert_close(st['max'], np.abs(e).max(0), 1e-6, 1e-3, 'ned max')
+
+
+def test_sim_vibration_env(gpu):
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    g = load_golden('philox_90deg_mid_rf1_vibrand.npz')
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=False)
+    sim = Sim([100.0, 0.0, 0.0], _traj(g), ref_frame=1, imu=imu,
+              env={'acc': '[0.03 0.001 0.01]-random', 'gyro': '[6 5 4]d-random'},
+              algorithm=FreeIntegration(g['ini']), seed=int(g['seed']))
+    sim.run(3)
+    st = sim.get_error_stats('pos', -1)
+    assert_close(st['avg'], g['stat_pos_avg'], 1e-6, 1e-3, 'avg')
+    assert_close(sim.get_data(['gyro'])[0][2], g['gyro'][2], 1e-12, 1.0, 'gyro')
+
+
+def test_sim_allan_and_foreign_plugins(gpu):
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.allan_analysis import Allan
+    g = load_golden('philox_90deg_low_rf1_run1000.npz')
+    imu = imu_model.IMU(accuracy='low-accuracy', axis=6, gps=False)
+    sim = Sim([100.0, 0.0, 0.0], _traj(g), ref_frame=1, imu=imu, algorithm=Allan(),
+              seed=int(g['seed']), run_base=1000)
+    sim.run(4)
+    tau, ada, adg = sim.get_data(['algo_time', 'ad_accel', 'ad_gyro'])
+    assert sorted(ada.keys()) == ['algo0_0', 'algo0_1', 'algo0_2', 'algo0_3']
+    for r in range(4):
+        for c in range(3):
+            av, t = onp.allan_var(g['accel'][r][:, c], 100.0)
+            assert_close(ada['algo0_%d' % r][:, c], np.sqrt(av), 1e-9, 0.0, 'ad_accel')
+            av, t = onp.allan_var(g['gyro'][r][:, c], 100.0)
+            assert_close(adg['algo0_%d' % r][:, c], np.sqrt(av), 1e-9, 0.0, 'ad_gyro')
+        assert_close(tau['algo0_%d' % r], t, 1e-15, 0.0, 'tau')
+
+    class MeanGyro(object):          # a reference-style plugin this engine knows nothing about
+        name = 'mean'
+
+        def __init__(self):
+            self.input = ['fs', 'gyro']
+            self.output = ['wb']
+            self.batch = True
+            self.results = None
+
+        def run(self, s):
+            self.results = [s[1].mean(0) * s[0]]
+
+        def get_results(self):
+            return self.results
+
+        def reset(self):
+            self.results = None
+    sim = Sim([100.0, 0.0, 0.0], _traj(g), ref_frame=1, imu=imu, algorithm=MeanGyro(),
+              seed=int(g['seed']), run_base=1000)
+    sim.run(2)
+    wb = sim.get_data(['wb'])[0]
+    assert sorted(wb.keys()) == ['mean_0', 'mean_1']
+    assert_close(wb['mean_1'], g['gyro'][1].mean(0) * 100.0, 1e-12, 1e-6, 'foreign plugin')

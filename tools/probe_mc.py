@@ -11,7 +11,37 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gnss_ins_sim_b200 import engine  # noqa: E402
 
 
+def one(runs, lanes, rf, reps):
+    """A single configuration, for runs under ncu."""
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden',
+                                  'traj_90deg_turn_100hz_rf%d.npz' % rf)))
+    mid_g = {'b': np.zeros(3), 'b_drift': np.full(3, 3.5 * np.pi / 180 / 3600),
+             'b_corr': np.full(3, 100.0), 'arw': np.full(3, 0.25 * np.pi / 180 / 60)}
+    mid_a = {'b': np.zeros(3), 'b_drift': np.full(3, 5e-5), 'b_corr': np.full(3, 100.0),
+             'vrw': np.full(3, 0.03 / 60)}
+    nav = np.concatenate([g['ref_att'], g['ref_pos'], g['ref_vel']], axis=1)
+    n = nav.shape[0]
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda()
+           for a in (g['ref_gyro'], g['ref_accel'], nav, g['ini'][None])]
+    cfg = engine.make_mc_config(rf, 100.0, n, runs, 1, mid_g, mid_a, 1, 9, lanes_per_run=lanes)
+    res = engine.mc_free_integration(cfg, *dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        engine.mc_free_integration(cfg, *dev, out=res)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(json.dumps({'rf': rf, 'runs': runs, 'n': n, 'lanes': lanes, 'ms': round(ms, 4),
+                      'run_steps_per_s': runs * n / (ms * 1e-3)}), flush=True)
+
+
 def main():
+    if len(sys.argv) > 1:
+        runs, lanes, rf = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+        one(runs, lanes, rf, int(sys.argv[4]) if len(sys.argv) > 4 else 3)
+        return
     g = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden',
                                   'traj_90deg_turn_100hz_rf1.npz')))
     g0 = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden',
