@@ -65,11 +65,6 @@ struct McParams {
   int64_t stats_start;
 };
 
-struct Sample {
-  double g[3], a[3];    // measurement without the GM drift
-  double zg[3], za[3];  // GM drive normals
-};
-
 struct TileSmem {
   alignas(128) double gyro[kStages][kTile * 3];
   alignas(128) double accel[kStages][kTile * 3];
@@ -139,14 +134,43 @@ __device__ __forceinline__ void noisy_triad(const TriadNoise& e, const double* r
   }
 }
 
+// Gauss-Markov drift of the G samples of a block, time-parallel: d[t+1] = a d[t] + b z[t] is an
+// affine recurrence, so the group runs an inclusive scan y_j = sum_{q<=j} a^(j-q) b z_q with
+// warp shuffles; d_j = a^j carry + y_(j-1) and the carry moves on by a^G carry + y_(G-1).
+template <int G>
+__device__ __forceinline__ double gm_block(double x, double a, double apj, double aG, int j,
+                                           double& carry) {
+  double y = x;
+  if (G > 1) {
+    double ap = a;
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, y, off, G);
+      if (j >= off) y = fma(ap, u, y);
+      ap *= ap;
+    }
+  }
+  double ym1 = 0.0, ylast = y;
+  if (G > 1) {
+    ym1 = __shfl_up_sync(0xffffffffu, y, 1, G);
+    if (j == 0) ym1 = 0.0;
+    ylast = __shfl_sync(0xffffffffu, y, G - 1, G);
+  }
+  const double d = (G > 1) ? fma(apj, carry, ym1) : carry;
+  carry = fma(aG, carry, ylast);
+  return d;
+}
+
 template <int G, int RF, bool FED, bool PROC>
 __global__ void __launch_bounds__(kThreads)
 mc_kernel(const __grid_constant__ McParams p) {
   __shared__ TileSmem sm;
   constexpr int kRunsPerWarp = 32 / G;
+  constexpr bool kSplit = (G >= 4);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int j = lane % G;
+  const int role = lane & 3;
   const int64_t run_raw =
       (static_cast<int64_t>(blockIdx.x) * kWarps + warp) * kRunsPerWarp + lane / G;
   const bool active = run_raw < p.runs;
@@ -154,6 +178,7 @@ mc_kernel(const __grid_constant__ McParams p) {
   const int64_t grun = p.run_offset + run;            // global run id
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
   const bool dump = active && run < p.dump_runs;
+  const bool warp_dumps = __any_sync(0xffffffffu, dump);
   constexpr bool kStaged = !FED || PROC;
 
   const int64_t num_tiles = (p.n + kTile - 1) / kTile;
@@ -178,7 +203,17 @@ mc_kernel(const __grid_constant__ McParams p) {
     const int64_t set = (irun < p.ini_sets) ? irun : 0;  // free_integration.py:85-87
     nav_init<RF>(st, p.ini + set * p.ini_rows, p.ini_rows);
   }
-  double dg[3] = {0.0, 0.0, 0.0}, da[3] = {0.0, 0.0, 0.0};  // GM drift, d[0] = 0
+  // Gauss-Markov drift carried across blocks (d[0] = 0), and the powers a^j, a^G
+  double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double apj[6], aG[6];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double aa = p.accel.gm_a[c], ag = p.gyro.gm_a[c];
+    apj[c] = (G > 1) ? pow(aa, static_cast<double>(j)) : 1.0;
+    apj[3 + c] = (G > 1) ? pow(ag, static_cast<double>(j)) : 1.0;
+    aG[c] = (G > 1) ? pow(aa, static_cast<double>(G)) : aa;
+    aG[3 + c] = (G > 1) ? pow(ag, static_cast<double>(G)) : ag;
+  }
   double phase[3] = {0.0, 0.0, 0.0};
   if (!FED && p.gyro.vib_type == 2) {
 #pragma unroll
@@ -215,64 +250,67 @@ mc_kernel(const __grid_constant__ McParams p) {
 
     for (int base = 0; base < cnt; base += G) {
       // ---------------- phase A: lane j prepares sample t0 + base + j --------------
-      Sample smp;
+      double mg[3], ma[3];  // the complete measurement of sample base + j
       const int tj = base + j;
       const int64_t t = t0 + tj;
-      if (tj < cnt) {
-        if (FED) {
+      if (FED) {
+        if (tj < cnt) {
           const int64_t o = run * p.sr + t * p.st;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            smp.g[c] = p.fed_gyro[o + c * p.sc];
-            smp.a[c] = p.fed_accel[o + c * p.sc];
-            smp.zg[c] = smp.za[c] = 0.0;
+            mg[c] = p.fed_gyro[o + c * p.sc];
+            ma[c] = p.fed_accel[o + c * p.sc];
           }
         } else {
-          noisy_triad(p.accel, &sm.accel[s][tj * 3], static_cast<uint32_t>(t), kDrawAccel, 0,
-                      run_lo, run_hi, p.k0, p.k1, run, phase, smp.a, smp.za);
-          noisy_triad(p.gyro, &sm.gyro[s][tj * 3], static_cast<uint32_t>(t), kDrawGyro, 1, run_lo,
-                      run_hi, p.k0, p.k1, run, phase, smp.g, smp.zg);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) mg[c] = ma[c] = 0.0;
         }
       } else {
+        double zg[3], za[3];
+        if (tj < cnt) {
+          noisy_triad(p.accel, &sm.accel[s][tj * 3], static_cast<uint32_t>(t), kDrawAccel, 0,
+                      run_lo, run_hi, p.k0, p.k1, run, phase, ma, za);
+          noisy_triad(p.gyro, &sm.gyro[s][tj * 3], static_cast<uint32_t>(t), kDrawGyro, 1, run_lo,
+                      run_hi, p.k0, p.k1, run, phase, mg, zg);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) smp.g[c] = smp.a[c] = smp.zg[c] = smp.za[c] = 0.0;
+          for (int c = 0; c < 3; ++c) mg[c] = ma[c] = zg[c] = za[c] = 0.0;
+        }
+        // + drift: the GM state d[t] (pathgen.py:583-590) or drift*z[t] if tau = inf (:591-593)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double da = gm_block<G>(p.accel.gm_b[c] * za[c], p.accel.gm_a[c], apj[c], aG[c], j,
+                                        carry[c]);
+          const double dg = gm_block<G>(p.gyro.gm_b[c] * zg[c], p.gyro.gm_a[c], apj[3 + c],
+                                        aG[3 + c], j, carry[3 + c]);
+          ma[c] += da + p.accel.wd[c] * za[c];
+          mg[c] += dg + p.gyro.wd[c] * zg[c];
+        }
+      }
+      if (warp_dumps && dump && tj < cnt && p.out_gyro) {
+        const int64_t o = run * p.osr + t * p.ost;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          p.out_gyro[o + c * p.osc] = mg[c];
+          p.out_accel[o + c * p.osc] = ma[c];
+        }
       }
 
       // ---------------- phase B: serial over the G samples of the block ------------
-      double keep[15];  // lane k keeps (gyro, accel) of sample base+k and the state after it
+      double keep[9];  // lane k keeps the state after sample base+k (history output)
 #pragma unroll
-      for (int c = 0; c < 15; ++c) keep[c] = 0.0;
+      for (int c = 0; c < 9; ++c) keep[c] = 0.0;
       const int kmax = min(G, cnt - base);
 #pragma unroll 1
       for (int k = 0; k < kmax; ++k) {
         const int64_t tk = t0 + base + k;
         Vec3 w, f;
         if (G == 1) {
-          w = Vec3{smp.g[0], smp.g[1], smp.g[2]};
-          f = Vec3{smp.a[0], smp.a[1], smp.a[2]};
+          w = Vec3{mg[0], mg[1], mg[2]};
+          f = Vec3{ma[0], ma[1], ma[2]};
         } else {
-          w = Vec3{shfl_grp<G>(smp.g[0], k), shfl_grp<G>(smp.g[1], k), shfl_grp<G>(smp.g[2], k)};
-          f = Vec3{shfl_grp<G>(smp.a[0], k), shfl_grp<G>(smp.a[1], k), shfl_grp<G>(smp.a[2], k)};
-        }
-        if (!FED) {
-          double zg[3], za[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            zg[c] = (G == 1) ? smp.zg[c] : shfl_grp<G>(smp.zg[c], k);
-            za[c] = (G == 1) ? smp.za[c] : shfl_grp<G>(smp.za[c], k);
-          }
-          // meas = ... + drift: d[t] (GM) or drift*z[t] (white drift), pathgen.py:583-593
-          w.x += dg[0] + p.gyro.wd[0] * zg[0];
-          w.y += dg[1] + p.gyro.wd[1] * zg[1];
-          w.z += dg[2] + p.gyro.wd[2] * zg[2];
-          f.x += da[0] + p.accel.wd[0] * za[0];
-          f.y += da[1] + p.accel.wd[1] * za[1];
-          f.z += da[2] + p.accel.wd[2] * za[2];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {  // d[t+1] = a d[t] + b z[t]
-            dg[c] = p.gyro.gm_a[c] * dg[c] + p.gyro.gm_b[c] * zg[c];
-            da[c] = p.accel.gm_a[c] * da[c] + p.accel.gm_b[c] * za[c];
-          }
+          w = Vec3{shfl_grp<G>(mg[0], k), shfl_grp<G>(mg[1], k), shfl_grp<G>(mg[2], k)};
+          f = Vec3{shfl_grp<G>(ma[0], k), shfl_grp<G>(ma[1], k), shfl_grp<G>(ma[2], k)};
         }
         if (PROC) {
           // error of sample tk (state BEFORE the step), ins_data_manager.py:536-541
@@ -302,37 +340,23 @@ mc_kernel(const __grid_constant__ McParams p) {
             ++pe_cnt;
           }
         }
-        if (j == k) {
-          keep[0] = w.x; keep[1] = w.y; keep[2] = w.z;
-          keep[3] = f.x; keep[4] = f.y; keep[5] = f.z;
-        }
         if (tk < p.n - 1) {
-          nav_step<RF>(st, w, f, p.dt, p.earth_rot != 0);
-          if (j == k) {
-            keep[6] = st.yaw; keep[7] = st.pitch; keep[8] = st.roll;
-            keep[9] = st.pos.x; keep[10] = st.pos.y; keep[11] = st.pos.z;
-            keep[12] = st.vel.x; keep[13] = st.vel.y; keep[14] = st.vel.z;
+          nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role);
+          if (warp_dumps && j == k) {
+            keep[0] = st.yaw; keep[1] = st.pitch; keep[2] = st.roll;
+            keep[3] = st.pos.x; keep[4] = st.pos.y; keep[5] = st.pos.z;
+            keep[6] = st.vel.x; keep[7] = st.vel.y; keep[8] = st.vel.z;
           }
         }
       }
-      // ---------------- histories: lane j writes sample base+j (meas) / +1 (state) --
-      if (dump && tj < cnt) {
-        if (p.out_gyro) {
-          const int64_t o = run * p.osr + t * p.ost;
+      // ---------------- histories: lane j writes the state of sample base+j+1 ---------
+      if (warp_dumps && dump && tj < cnt && p.out_att && t + 1 < p.n) {
+        const int64_t o = run * p.osr + (t + 1) * p.ost;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            p.out_gyro[o + c * p.osc] = keep[c];
-            p.out_accel[o + c * p.osc] = keep[3 + c];
-          }
-        }
-        if (p.out_att && t + 1 < p.n) {
-          const int64_t o = run * p.osr + (t + 1) * p.ost;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            p.out_att[o + c * p.osc] = keep[6 + c];
-            p.out_pos[o + c * p.osc] = keep[9 + c];
-            p.out_vel[o + c * p.osc] = keep[12 + c];
-          }
+        for (int c = 0; c < 3; ++c) {
+          p.out_att[o + c * p.osc] = keep[c];
+          p.out_pos[o + c * p.osc] = keep[3 + c];
+          p.out_vel[o + c * p.osc] = keep[6 + c];
         }
       }
     }

@@ -21,11 +21,22 @@ struct SinCos3 {
   double sy, cy, sp, cp, sr, cr;  // yaw, pitch, roll
 };
 
+// Full-range fallback, kept out of line: only reached when an angle left [-64, 64], i.e.
+// after the Euler-angle singularity blew a rate up.
+__device__ __noinline__ void sincos_full(double x, double* s, double* c) { sincos(x, s, c); }
+
+__device__ __forceinline__ void sincos_angle(double x, double* s, double* c) {
+  if (fabs(x) <= 64.0)
+    sincos_bounded(x, s, c);
+  else
+    sincos_full(x, s, c);
+}
+
 __device__ __forceinline__ SinCos3 sincos3(double yaw, double pitch, double roll) {
   SinCos3 t;
-  sincos(yaw, &t.sy, &t.cy);
-  sincos(pitch, &t.sp, &t.cp);
-  sincos(roll, &t.sr, &t.cr);
+  sincos_angle(yaw, &t.sy, &t.cy);
+  sincos_angle(pitch, &t.sp, &t.cp);
+  sincos_angle(roll, &t.sr, &t.cr);
   return t;
 }
 
@@ -57,13 +68,14 @@ __device__ __forceinline__ Vec3 cross3(const Vec3& a, const Vec3& b) {
   return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 
-// geoparams.geo_param: geoparams.py:25-53
+// geoparams.geo_param: geoparams.py:25-53, given sin/cos of the latitude
 struct GeoParam {
   double rm, rn, g, sl, cl;
 };
-__device__ __forceinline__ GeoParam geo_param(double lat, double h) {
+__device__ __forceinline__ GeoParam geo_param_sc(double sl, double cl, double h) {
   GeoParam p;
-  sincos(lat, &p.sl, &p.cl);
+  p.sl = sl;
+  p.cl = cl;
   const double sl_sqr = p.sl * p.sl;
   const double q = 1.0 - kESqr * sl_sqr;
   const double sq = sqrt(q);
@@ -74,12 +86,17 @@ __device__ __forceinline__ GeoParam geo_param(double lat, double h) {
               3.0 * h * h / kRe / kRe);
   return p;
 }
+__device__ __forceinline__ GeoParam geo_param(double lat, double h) {
+  double sl, cl;
+  sincos_angle(lat, &sl, &cl);
+  return geo_param_sc(sl, cl, h);
+}
 
 // geoparams.lla2ecef: geoparams.py:70-87
 __device__ __forceinline__ Vec3 lla2ecef(double lat, double lon, double alt) {
   double sl, cl, so, co;
-  sincos(lat, &sl, &cl);
-  sincos(lon, &so, &co);
+  sincos_angle(lat, &sl, &cl);
+  sincos_angle(lon, &so, &co);
   const double r = kRe / sqrt(1.0 - kESqr * sl * sl);
   const double rho = (r + alt) * cl;
   return Vec3{rho * co, rho * so, (r * (1.0 - kESqr) + alt) * sl};
@@ -98,12 +115,43 @@ struct NavState {
   double yaw, pitch, roll;
   SinCos3 sc;  // sin/cos of (yaw, pitch, roll): euler2dcm(att[i]) of step i IS the
                // cos/sin euler_update_zyx needs at step i+1, so it is computed once
+  double sl, cl;  // sin/cos of the latitude (ref_frame 0): geo_param of the NEXT step
   Vec3 vel_b;  // body velocity   (ref_frame 1 state)
   Vec3 vel;    // NED velocity    (ref_frame 0 state; ref_frame 1 output)
   Vec3 pos;    // ECEF-offset xyz (ref_frame 1) or lat, lon, alt (ref_frame 0)
   double g;    // gravity: geo_param(r0) or the ini override
   bool fixed_g;  // false: ref_frame 0 without override -> geo_param(pos) every step
 };
+
+// Refresh the cached sin/cos after the angles (and the latitude) moved.
+// SPLIT (lane groups of >= 4 lanes): the state is replicated across the group, so the
+// three (four with the latitude) independent sincos evaluations are spread over the lanes
+// of each 4-lane subgroup -- lane role q evaluates angle q -- and exchanged by shuffles:
+// one sincos worth of instruction issue instead of three or four.
+template <int RF, bool SPLIT>
+__device__ __forceinline__ void refresh_trig(NavState& s, int role) {
+  if (!SPLIT) {
+    s.sc = sincos3(s.yaw, s.pitch, s.roll);
+    if (RF == 0) sincos_angle(s.pos.x, &s.sl, &s.cl);
+  } else {
+    double a = s.roll;
+    if (role == 0) a = s.yaw;
+    if (role == 1) a = s.pitch;
+    if (RF == 0 && role == 3) a = s.pos.x;
+    double sv, cv;
+    sincos_angle(a, &sv, &cv);
+    s.sc.sy = __shfl_sync(0xffffffffu, sv, 0, 4);
+    s.sc.cy = __shfl_sync(0xffffffffu, cv, 0, 4);
+    s.sc.sp = __shfl_sync(0xffffffffu, sv, 1, 4);
+    s.sc.cp = __shfl_sync(0xffffffffu, cv, 1, 4);
+    s.sc.sr = __shfl_sync(0xffffffffu, sv, 2, 4);
+    s.sc.cr = __shfl_sync(0xffffffffu, cv, 2, 4);
+    if (RF == 0) {
+      s.sl = __shfl_sync(0xffffffffu, sv, 3, 4);
+      s.cl = __shfl_sync(0xffffffffu, cv, 3, 4);
+    }
+  }
+}
 
 // free_integration.py:96-102 / :126-132 -- sample 0
 template <int RF>
@@ -114,9 +162,7 @@ __device__ __forceinline__ void nav_init(NavState& s, const double* __restrict__
   s.yaw = ini[6];
   s.pitch = ini[7];
   s.roll = ini[8];
-  s.sc = sincos3(s.yaw, s.pitch, s.roll);
-  const Dcm c = dcm_from_sincos(s.sc);
-  s.vel = mul_t(c, s.vel_b);
+  s.sl = s.cl = 0.0;
   if (RF == 1) {
     s.pos = lla2ecef(lat, lon, alt);
     s.g = (ini_rows > 9) ? ini[9] : geo_param(lat, alt).g;  // free_integration.py:89-93
@@ -126,6 +172,9 @@ __device__ __forceinline__ void nav_init(NavState& s, const double* __restrict__
     s.fixed_g = ini_rows > 9;  // free_integration.py:143-146
     s.g = s.fixed_g ? ini[9] : 0.0;
   }
+  refresh_trig<RF, false>(s, 0);
+  const Dcm c = dcm_from_sincos(s.sc);
+  s.vel = mul_t(c, s.vel_b);
 }
 
 // attitude.euler_update_zyx (attitude.py:679-721) using the cached sin/cos of the
@@ -161,9 +210,9 @@ __device__ __forceinline__ void euler_update(NavState& s, const Vec3& w, double 
 }
 
 // One step i-1 -> i with the measurements of sample i-1.
-template <int RF>
+template <int RF, bool SPLIT>
 __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel,
-                                         double dt, bool earth_rot) {
+                                         double dt, bool earth_rot, int role) {
   if (RF == 1) {
     // free_integration.py:104-116
     // c_bn.dot(g_n) with g_n = [0,0,g]: third column of the OLD dcm, from the old sin/cos
@@ -174,7 +223,7 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     s.vel_b.x = s.vel_b.x + (accel.x + cg.x) * dt - wxv.x * dt;
     s.vel_b.y = s.vel_b.y + (accel.y + cg.y) * dt - wxv.y * dt;
     s.vel_b.z = s.vel_b.z + (accel.z + cg.z) * dt - wxv.z * dt;
-    s.sc = sincos3(s.yaw, s.pitch, s.roll);
+    refresh_trig<RF, SPLIT>(s, role);
     const Dcm c = dcm_from_sincos(s.sc);
     s.vel = mul_t(c, s.vel_b);
     s.pos.x += vel_old.x * dt;
@@ -182,7 +231,7 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     s.pos.z += vel_old.z * dt;
   } else {
     // free_integration.py:133-172
-    const GeoParam p = geo_param(s.pos.x, s.pos.z);
+    const GeoParam p = geo_param_sc(s.sl, s.cl, s.pos.z);
     const double rm_e = p.rm + s.pos.z;
     const double rn_e = p.rn + s.pos.z;
     const double g = s.fixed_g ? s.g : p.g;
@@ -207,7 +256,7 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     s.pos.x += vel_old.x / rm_e * dt;
     s.pos.y += vel_old.y / rn_e / p.cl * dt;
     s.pos.z += (-vel_old.z) * dt;
-    s.sc = sincos3(s.yaw, s.pitch, s.roll);
+    refresh_trig<RF, SPLIT>(s, role);
     // vel_b[i] = c_bn(i).dot(vel[i]) (:172) is not an output of the plugin; not computed
   }
 }

@@ -229,7 +229,8 @@ def test_k2_pitch_reflection_and_wrap(eng):
             assert np.abs(wrap_pi(a - o_att)).max() < 1e-9
             assert_close(vel.cpu().numpy(), o_vel, 1e-9, 1.0, 'vel')
             assert (np.abs(a[:, :, 1]) <= np.pi / 2 + 1e-12).all()
-            assert (np.abs(a[:, :, [0, 2]]) <= np.pi + 1e-12).all()
+            # yaw / roll get ONE +-2pi wrap per step, not a modulo (attitude.py:712-720): near
+            # the singularity a single step can move them by more than 2pi, as in the reference
     # the scenario really exercises the branches
     d_pitch = np.abs(np.diff(o_att[:, :, 1], axis=1))
     flipped = (np.abs(np.abs(np.diff(o_att[:, :, 0], axis=1)) - np.pi) < 0.5).any(1)
