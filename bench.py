@@ -309,8 +309,10 @@ def run_b200(args):
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     e2e_value = total_runs * n * args.steps / float(t.item())
-    h2d = (n * 15 + 9) * 8            # trajectory (gyro, accel, nav) + initial state
-    d2h = 27 * 8                      # the [3][9] statistics
+    # plan path (N = 1): true IMU samples + last ref_nav row + initial state up,
+    # statistics + per-run end-point errors down
+    h2d = (n * 6 + 9 + 9) * 8
+    d2h = (27 + R * 9) * 8
 
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -324,7 +326,8 @@ def run_b200(args):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'api': 'gnss_ins_sim_b200.sim.Sim.run + get_error_stats'},
-        'gpu_launches': args.steps * 7,    # mc_kernel + 6 statistics kernels per step
+        # per step: mc_kernel + stats_small_kernel (N = 1) or + 2x(stage1, stage2) (N > 1)
+        'gpu_launches': args.steps * (2 if world == 1 else 5),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': None,
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',

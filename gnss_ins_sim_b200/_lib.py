@@ -57,6 +57,9 @@ SIGNATURES = {
     'b2ins_imu_noise_f64_host': (_I, [_D, _L, _L, _P, _P, _SE, _SE, _VB, _VB, _U64, _L, _I, _P, _P, _P]),
     'b2ins_mc_free_integration_f64': (_I, [_MC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'b2ins_mc_free_integration_f64_host': (_I, [_MC, _P, _P, _P, _P, _P, _P]),
+    'b2ins_mc_plan_create': (_I, [_L, _L, _I, _I, ctypes.POINTER(ctypes.c_void_p)]),
+    'b2ins_mc_plan_run': (_I, [_P, _MC, _P, _P, _P, _P, _P, _P]),
+    'b2ins_mc_plan_destroy': (_I, [_P]),
     'b2ins_error_stats_workspace_bytes': (_L, [_I]),
     'b2ins_error_partial_f64': (_I, [_L, _I, _P, _P, _P, _P]),
     'b2ins_error_partial2_f64': (_I, [_L, _I, _P, _P, _P, _P, _P]),

@@ -462,6 +462,113 @@ int b2ins_mc_free_integration_f64_host(const b2ins_mc_config* cfg, const double*
   return B2INS_OK;
 }
 
+// ---------------------------------------------------------------- plan ------
+struct b2ins_mc_plan {
+  int64_t n = 0, max_runs = 0;
+  int ini_sets = 0, ini_rows = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  double* d_in = nullptr;    // [n*3 gyro][n*3 accel][n*9 nav][sets*rows ini]
+  double* d_out = nullptr;   // [27 stats][max_runs*9 end_err]
+  double* d_ws = nullptr;
+  double* h_in = nullptr;    // pinned: [n*3][n*3][9 last nav row][sets*rows]
+  double* h_out = nullptr;   // pinned: [27][max_runs*9]
+  // sub-buffers start on 16-byte boundaries (bulk async copies): offsets in doubles
+  size_t n3p() const { return (static_cast<size_t>(n) * 3 + 1) & ~size_t(1); }
+  size_t n9p() const { return (static_cast<size_t>(n) * 9 + 1) & ~size_t(1); }
+  size_t in_doubles() const { return 2 * n3p() + n9p() + static_cast<size_t>(ini_sets) * ini_rows; }
+};
+
+int b2ins_mc_plan_destroy(b2ins_mc_plan* plan) {
+  if (!plan) return B2INS_OK;
+  if (plan->d_in) cudaFree(plan->d_in);
+  if (plan->d_out) cudaFree(plan->d_out);
+  if (plan->d_ws) cudaFree(plan->d_ws);
+  if (plan->h_in) cudaFreeHost(plan->h_in);
+  if (plan->h_out) cudaFreeHost(plan->h_out);
+  if (plan->stream) cudaStreamDestroy(plan->stream);
+  delete plan;
+  return B2INS_OK;
+}
+
+int b2ins_mc_plan_create(int64_t n, int64_t max_runs, int ini_sets, int ini_rows,
+                         b2ins_mc_plan** out) {
+  ARG_CHECK(out, "null plan pointer");
+  *out = nullptr;
+  ARG_CHECK(n > 0 && max_runs > 0, "n and max_runs must be positive");
+  ARG_CHECK(n < (int64_t(1) << 32), "n must be < 2^32");
+  ARG_CHECK(ini_sets >= 1 && (ini_rows == 9 || ini_rows == 10), "ini must be [sets>=1][9|10]");
+  b2ins_mc_plan* p = new b2ins_mc_plan();
+  p->n = n;
+  p->max_runs = max_runs;
+  p->ini_sets = ini_sets;
+  p->ini_rows = ini_rows;
+  const size_t in_bytes = p->in_doubles() * sizeof(double);
+  const size_t stage_bytes = (2 * p->n3p() + 9 + static_cast<size_t>(ini_sets) * ini_rows) * sizeof(double);
+  const size_t out_bytes = (27 + static_cast<size_t>(max_runs) * 9) * sizeof(double);
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_in, in_bytes + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_out, out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_ws, static_cast<size_t>(b2ins_error_stats_workspace_bytes(9)));
+  if (e == cudaSuccess) e = cudaMallocHost(&p->h_in, stage_bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&p->h_out, out_bytes);
+  if (e != cudaSuccess) {
+    b2ins_mc_plan_destroy(p);
+    return fail(B2INS_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return B2INS_OK;
+}
+
+int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const double* ref_gyro,
+                      const double* ref_accel, const double* ref_nav, const double* ini,
+                      double* end_err, double* stats) {
+  ARG_CHECK(plan && cfg, "null plan / cfg");
+  ARG_CHECK(cfg->n == plan->n && cfg->runs >= 1 && cfg->runs <= plan->max_runs &&
+                cfg->ini_sets == plan->ini_sets && cfg->ini_rows == plan->ini_rows,
+            "cfg does not fit the plan (n=%lld runs<=%lld ini=[%d][%d])",
+            static_cast<long long>(plan->n), static_cast<long long>(plan->max_runs), plan->ini_sets,
+            plan->ini_rows);
+  ARG_CHECK(ref_gyro && ref_accel && ref_nav && ini && stats, "null buffer");
+  ARG_CHECK(cfg->stats_start < 0 && cfg->dump_runs == 0,
+            "a plan computes end-point errors and their statistics only");
+  const int64_t n = plan->n;
+  const size_t n3 = static_cast<size_t>(n) * 3;
+  const size_t ini_d = static_cast<size_t>(plan->ini_sets) * plan->ini_rows;
+  // stage: gyro | accel | last nav row | ini  (gyro/accel at the device offsets)
+  const size_t n3p = plan->n3p();
+  std::memcpy(plan->h_in, ref_gyro, n3 * sizeof(double));
+  std::memcpy(plan->h_in + n3p, ref_accel, n3 * sizeof(double));
+  std::memcpy(plan->h_in + 2 * n3p, ref_nav + (n - 1) * 9, 9 * sizeof(double));
+  std::memcpy(plan->h_in + 2 * n3p + 9, ini, ini_d * sizeof(double));
+  double* d_gyro = plan->d_in;
+  double* d_accel = plan->d_in + n3p;
+  double* d_nav = plan->d_in + 2 * n3p;
+  double* d_ini = d_nav + plan->n9p();
+  // the IMU block is contiguous on both sides: one copy; the nav row and ini are small
+  CU_CHECK(cudaMemcpyAsync(d_gyro, plan->h_in, (n3p + n3) * sizeof(double), cudaMemcpyHostToDevice,
+                           plan->stream));
+  CU_CHECK(cudaMemcpyAsync(d_nav + (n - 1) * 9, plan->h_in + 2 * n3p, 9 * sizeof(double),
+                           cudaMemcpyHostToDevice, plan->stream));
+  CU_CHECK(cudaMemcpyAsync(d_ini, plan->h_in + 2 * n3p + 9, ini_d * sizeof(double),
+                           cudaMemcpyHostToDevice, plan->stream));
+  double* d_stats = plan->d_out;
+  double* d_err = plan->d_out + 27;
+  int rc = b2ins_mc_free_integration_f64(cfg, d_gyro, d_accel, d_nav, d_ini, d_err, nullptr,
+                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                         plan->stream);
+  if (rc != B2INS_OK) return rc;
+  rc = b2ins_error_stats_f64(cfg->runs, 9, d_err, d_stats, plan->d_ws, plan->stream);
+  if (rc != B2INS_OK) return rc;
+  const size_t out_d = 27 + (end_err ? static_cast<size_t>(cfg->runs) * 9 : 0);
+  CU_CHECK(cudaMemcpyAsync(plan->h_out, plan->d_out, out_d * sizeof(double), cudaMemcpyDeviceToHost,
+                           plan->stream));
+  CU_CHECK(cudaStreamSynchronize(plan->stream));
+  std::memcpy(stats, plan->h_out, 27 * sizeof(double));
+  if (end_err) std::memcpy(end_err, plan->h_out + 27, static_cast<size_t>(cfg->runs) * 9 * sizeof(double));
+  return B2INS_OK;
+}
+
 // ---------------------------------------------------------------- K3 --------
 int64_t b2ins_error_stats_workspace_bytes(int ncomp) {
   if (ncomp < 1) return 0;
@@ -512,6 +619,11 @@ int b2ins_error_stats_f64(int64_t runs, int ncomp, const double* err, double* st
   ARG_CHECK(runs > 0 && ncomp >= 1 && ncomp <= kStatMaxComp, "bad runs/ncomp");
   ARG_CHECK(err && stats && workspace, "null buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (runs * ncomp <= kStatSmallMax) {
+    stats_small_kernel<<<1, kStatSmallThreads, 0, s>>>(runs, ncomp, err, stats);
+    CU_CHECK(cudaGetLastError());
+    return B2INS_OK;
+  }
   double* ws = static_cast<double*>(workspace);
   double* partial = ws + static_cast<int64_t>(kStatBlocks) * 2 * ncomp;  // [2nc]
   double* partial2 = partial + 2 * ncomp;                                // [nc]

@@ -65,10 +65,11 @@ struct McParams {
   int64_t stats_start;
 };
 
+template <bool PROC>
 struct TileSmem {
   alignas(128) double gyro[kStages][kTile * 3];
   alignas(128) double accel[kStages][kTile * 3];
-  alignas(128) double nav[kStages][kTile * 9];
+  alignas(128) double nav[kStages][PROC ? kTile * 9 : 2];  // only staged for process statistics
   alignas(8) uint64_t full[kStages];
   alignas(8) uint64_t empty[kStages];
 };
@@ -76,7 +77,7 @@ struct TileSmem {
 // Issue the copies of one tile: the 16-byte-multiple part by bulk async copy (TMA)
 // completing on full[s]; an odd sample count leaves one 8-byte tail copied by hand.
 template <bool FED, bool PROC>
-__device__ __forceinline__ void issue_tile(TileSmem& sm, const McParams& p, int64_t tile, int s) {
+__device__ __forceinline__ void issue_tile(TileSmem<PROC>& sm, const McParams& p, int64_t tile, int s) {
   const int64_t t0 = tile * kTile;
   const uint32_t cnt = static_cast<uint32_t>(min64(kTile, p.n - t0));
   uint32_t tx = 0;
@@ -161,10 +162,29 @@ __device__ __forceinline__ double gm_block(double x, double a, double apj, doubl
   return d;
 }
 
+// a^e for a small non-negative integer e (binary powering; no libm call, no stack frame)
+__device__ __forceinline__ double ipow(double a, int e) {
+  double r = 1.0, b = a;
+#pragma unroll
+  for (int bit = 0; bit < 6; ++bit) {
+    if ((e >> bit) & 1) r *= b;
+    b *= b;
+  }
+  return r;
+}
+
+// resident CTAs per SM the register allocation must allow: the throughput configuration
+// (G = 1) wants many warps per scheduler to cover FP64 latency; wide groups are latency bound
+// by the serial recurrence and keep their registers
+template <int G>
+struct MinBlocks {
+  static constexpr int value = (G == 1) ? 4 : (G == 2 ? 3 : 2);
+};
+
 template <int G, int RF, bool FED, bool PROC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MinBlocks<G>::value)
 mc_kernel(const __grid_constant__ McParams p) {
-  __shared__ TileSmem sm;
+  __shared__ TileSmem<PROC> sm;
   constexpr int kRunsPerWarp = 32 / G;
   constexpr bool kSplit = (G >= 4);
   const int lane = threadIdx.x & 31;
@@ -209,10 +229,10 @@ mc_kernel(const __grid_constant__ McParams p) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const double aa = p.accel.gm_a[c], ag = p.gyro.gm_a[c];
-    apj[c] = (G > 1) ? pow(aa, static_cast<double>(j)) : 1.0;
-    apj[3 + c] = (G > 1) ? pow(ag, static_cast<double>(j)) : 1.0;
-    aG[c] = (G > 1) ? pow(aa, static_cast<double>(G)) : aa;
-    aG[3 + c] = (G > 1) ? pow(ag, static_cast<double>(G)) : ag;
+    apj[c] = (G > 1) ? ipow(aa, j) : 1.0;
+    apj[3 + c] = (G > 1) ? ipow(ag, j) : 1.0;
+    aG[c] = (G > 1) ? ipow(aa, G) : aa;
+    aG[3 + c] = (G > 1) ? ipow(ag, G) : ag;
   }
   double phase[3] = {0.0, 0.0, 0.0};
   if (!FED && p.gyro.vib_type == 2) {
@@ -246,7 +266,16 @@ mc_kernel(const __grid_constant__ McParams p) {
     const uint32_t parity = static_cast<uint32_t>((tile / kStages) & 1);
     const int64_t t0 = tile * kTile;
     const int cnt = static_cast<int>(min64(kTile, p.n - t0));
-    if (kStaged) mbar_wait(&sm.full[s], parity);
+    if (kStaged) {
+      // refill the stage the PREVIOUS tile used (all warps have had a whole tile to release
+      // it, so the producer thread hardly ever waits), then wait for this tile's data
+      if (threadIdx.x == 0 && tile >= 1 && tile - 1 + kStages < num_tiles) {
+        const int sp = static_cast<int>((tile - 1) % kStages);
+        mbar_wait(&sm.empty[sp], static_cast<uint32_t>(((tile - 1) / kStages) & 1));
+        issue_tile<FED, PROC>(sm, p, tile - 1 + kStages, sp);
+      }
+      mbar_wait(&sm.full[s], parity);
+    }
 
     for (int base = 0; base < cnt; base += G) {
       // ---------------- phase A: lane j prepares sample t0 + base + j --------------
@@ -364,10 +393,6 @@ mc_kernel(const __grid_constant__ McParams p) {
     if (kStaged) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[s]);
-      if (threadIdx.x == 0 && tile + kStages < num_tiles) {
-        mbar_wait(&sm.empty[s], parity);
-        issue_tile<FED, PROC>(sm, p, tile + kStages, s);
-      }
     }
   }
 

@@ -21,15 +21,13 @@ struct SinCos3 {
   double sy, cy, sp, cp, sr, cr;  // yaw, pitch, roll
 };
 
-// Full-range fallback, kept out of line: only reached when an angle left [-64, 64], i.e.
-// after the Euler-angle singularity blew a rate up.
-__device__ __noinline__ void sincos_full(double x, double* s, double* c) { sincos(x, s, c); }
-
+// sin/cos of an angle that normally lives in [-pi, pi] (Euler angles after their wrap,
+// latitude, longitude).  Outside [-64, 64] -- only reachable when the Euler-angle singularity
+// at pitch = +-pi/2 has blown a rate up, where the recurrence is meaningless anyway -- the
+// argument is first folded by a plain x - 2pi*rint(x/2pi); branch-free, no libm call.
 __device__ __forceinline__ void sincos_angle(double x, double* s, double* c) {
-  if (fabs(x) <= 64.0)
-    sincos_bounded(x, s, c);
-  else
-    sincos_full(x, s, c);
+  const double folded = fma(-kTwoPi, rint(x * (1.0 / kTwoPi)), x);
+  sincos_bounded(fabs(x) <= 64.0 ? x : folded, s, c);
 }
 
 __device__ __forceinline__ SinCos3 sincos3(double yaw, double pitch, double roll) {

@@ -77,4 +77,55 @@ __global__ void stats_std_kernel(int64_t runs, int ncomp, const double* __restri
   stats[2 * ncomp + c] = sqrt(partial2[c] / static_cast<double>(runs));
 }
 
+// Small ensembles (runs * ncomp <= kStatSmallMax): everything in ONE block and one launch --
+// sum/max, mean, second pass, std -- with the same fixed-order folding as the staged path.
+constexpr int kStatSmallMax = 1 << 17;
+constexpr int kStatSmallThreads = 1024;
+
+__global__ void __launch_bounds__(kStatSmallThreads)
+stats_small_kernel(int64_t runs, int ncomp, const double* __restrict__ err, double* __restrict__ stats) {
+  __shared__ double sh[2 * kStatSmallThreads];
+  __shared__ double mean_sh[kStatMaxComp];
+  const int threads = (kStatSmallThreads / ncomp) * ncomp;   // a multiple of ncomp
+  const int c = threadIdx.x % ncomp;
+  const int64_t total = runs * ncomp;
+  const bool on = threadIdx.x < threads;
+  double acc = 0.0, mx = 0.0;
+  if (on)
+    for (int64_t i = threadIdx.x; i < total; i += threads) {
+      const double e = err[i];
+      acc += e;
+      mx = fmax(mx, fabs(e));
+    }
+  sh[threadIdx.x] = acc;
+  sh[kStatSmallThreads + threadIdx.x] = mx;
+  __syncthreads();
+  if (threadIdx.x < ncomp) {
+    double s = 0.0, m = 0.0;
+    for (int k = threadIdx.x; k < threads; k += ncomp) {
+      s += sh[k];
+      m = fmax(m, sh[kStatSmallThreads + k]);
+    }
+    stats[c] = m;
+    const double mean = s / static_cast<double>(runs);
+    stats[ncomp + c] = mean;
+    mean_sh[c] = mean;
+  }
+  __syncthreads();
+  const double mu = mean_sh[c];
+  acc = 0.0;
+  if (on)
+    for (int64_t i = threadIdx.x; i < total; i += threads) {
+      const double d = err[i] - mu;
+      acc += d * d;
+    }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < ncomp) {
+    double s = 0.0;
+    for (int k = threadIdx.x; k < threads; k += ncomp) s += sh[k];
+    stats[2 * ncomp + c] = sqrt(s / static_cast<double>(runs));
+  }
+}
+
 }  // namespace b2ins

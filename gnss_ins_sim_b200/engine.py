@@ -163,6 +163,61 @@ def mc_free_integration(cfg, ref_gyro, ref_accel, ref_nav, ini, want_state=False
     return res
 
 
+class McPlan:
+    """b2ins_mc_plan: persistent device + pinned buffers and a stream for one experiment
+    shape; run() = stage, H2D, K12, K3, D2H, sync (the low-latency host path of Sim.run)."""
+
+    def __init__(self, n, max_runs, ini_sets, ini_rows):
+        _require_cuda()
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.n, self.max_runs, self.ini_sets, self.ini_rows = int(n), int(max_runs), int(ini_sets), int(ini_rows)
+        self.device = torch.cuda.current_device()
+        _lib.check(self._lib.b2ins_mc_plan_create(self.n, self.max_runs, self.ini_sets,
+                                                  self.ini_rows, ctypes.byref(self._h)))
+
+    def run(self, cfg, ref_gyro, ref_accel, ref_nav, ini, want_err=True):
+        """Host float64 C-contiguous arrays in; (end_err [runs,9] or None, stats [3,9]) out."""
+        hp = _lib.host_ptr
+        stats = np.empty((3, 9))
+        err = np.empty((cfg.runs, 9)) if want_err else None
+        _lib.check(self._lib.b2ins_mc_plan_run(self._h, ctypes.byref(cfg), hp(ref_gyro), hp(ref_accel),
+                                               hp(ref_nav), hp(ini), hp(err), hp(stats)))
+        return err, stats
+
+    def close(self):
+        if self._h:
+            self._lib.b2ins_mc_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_plan_cache = {}
+
+
+def get_plan(n, runs, ini_sets, ini_rows):
+    """A cached plan that fits (n, runs, ini layout) on the current device."""
+    _require_cuda()
+    key = (torch.cuda.current_device(), int(n), int(ini_sets), int(ini_rows))
+    plan = _plan_cache.get(key)
+    if plan is None or plan.max_runs < runs:
+        if plan is not None:
+            plan.close()
+        plan = McPlan(n, runs, ini_sets, ini_rows)
+        _plan_cache[key] = plan
+    return plan
+
+
+def f64c(a):
+    """C-contiguous float64 numpy view/copy of a."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
 _ws_cache = {}
 
 

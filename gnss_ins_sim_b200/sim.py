@@ -241,7 +241,7 @@ class Sim(object):
         self.data = {}          # name -> ndarray | dict-of-runs | LazyRuns
         self.err_stats = {}     # end-point ensemble statistics of the last run()
         self._traj = None
-        self._dev = None
+        self._dev_cache = None
         self._cache = {}
 
     # ---- names ------------------------------------------------------------
@@ -273,10 +273,20 @@ class Sim(object):
         d['fs'], d['ref_frame'], d['time'] = self.fs[0], self.ref_frame, traj['time']
         d['ref_pos'], d['ref_vel'], d['ref_att_euler'] = traj['ref_pos'], traj['ref_vel'], traj['ref_att']
         d['ref_accel'], d['ref_gyro'] = traj['ref_accel'], traj['ref_gyro']
-        nav = np.concatenate([traj['ref_att'], traj['ref_pos'], traj['ref_vel']], axis=1)
-        self._dev = {'ref_gyro': engine.to_device(traj['ref_gyro']),
-                     'ref_accel': engine.to_device(traj['ref_accel']),
-                     'ref_nav': engine.to_device(nav)}
+        self._nav = np.ascontiguousarray(
+            np.concatenate([traj['ref_att'], traj['ref_pos'], traj['ref_vel']], axis=1))
+        self._dev_cache = None
+
+    @property
+    def _dev(self):
+        """The trajectory on the device (made on first use: the single-GPU run() goes through
+        a plan that stages the host arrays itself)."""
+        if self._dev_cache is None:
+            t = self._traj
+            self._dev_cache = {'ref_gyro': engine.to_device(t['ref_gyro']),
+                               'ref_accel': engine.to_device(t['ref_accel']),
+                               'ref_nav': engine.to_device(self._nav)}
+        return self._dev_cache
 
     # ---- run ----------------------------------------------------------------
     def run(self, num_times=1):
@@ -331,17 +341,26 @@ class Sim(object):
     def _run_free_integration(self, i, algo):
         name = self.algo_name(i)
         lo, hi = self._shard
-        d = self._dev
-        self._mc[i] = {'base': algo.run_times, 'res': None}   # plugin's run counter at run 0
-        res = None
-        if hi > lo:
+        self._mc[i] = {'base': algo.run_times, 'end_err': None}   # plugin's run counter at run 0
+        if dist.world() == 1:
+            # single GPU: the plan path (pinned staging, one H2D, K12, K3, one D2H)
             cfg = self._mc_config(i, hi - lo, lo)
-            res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
-                                             algo.ini_device(), want_state=True)
+            t = self._traj
+            plan = engine.get_plan(cfg.n, cfg.runs, cfg.ini_sets, cfg.ini_rows)
+            err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav, algo.ini_sets)
+            self._mc[i]['end_err'] = err
+            self.err_stats[name] = stats
+        else:
+            d = self._dev
+            res = None
+            if hi > lo:
+                cfg = self._mc_config(i, hi - lo, lo)
+                res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
+                                                 algo.ini_device())
+            self.err_stats[name] = dist.ensemble_stats(res.end_err if res is not None else None,
+                                                       self.sim_count)
+            self._mc[i]['end_err'] = res.end_err.cpu().numpy() if res is not None else np.zeros((0, 9))
         algo.run_times += self.sim_count
-        self._mc[i]['res'] = res
-        self.err_stats[name] = dist.ensemble_stats(res.end_err if res is not None else None,
-                                                   self.sim_count)
         keys = ['%s_%d' % (name, k) for k in range(self.sim_count)]
         run_of = {k: r for r, k in enumerate(keys)}
         for out in ('att_euler', 'pos', 'vel'):
@@ -448,11 +467,10 @@ class Sim(object):
 
     def end_point_errors(self, algo_index=0):
         '''
-        [R_local, 9] end-point errors (att wrapped [rad], pos, vel) of this rank's runs, as a
-        CUDA tensor -- 72 bytes per run, the raw material of the ensemble statistics.
+        [R_local, 9] end-point errors (att wrapped [rad], pos, vel) of this rank's runs
+        (numpy) -- 72 bytes per run, the raw material of the ensemble statistics.
         '''
-        res = self._mc[algo_index]['res']
-        return res.end_err if res is not None else None
+        return self._mc[algo_index]['end_err']
 
     def get_error_stats(self, data_name, err_stats_start=-1, angle=False, use_output_units=False,
                         extra_opt='', algo_index=0):
@@ -493,10 +511,12 @@ class Sim(object):
 
     def _end_point_pos_stats(self, opt, algo_index):
         """'ned' / 'ecef' position error of LLA results, ins_data_manager.py:543-552."""
-        res = self._mc[algo_index]['res']
-        state = dist.gather_rows(res.end_state if res is not None else None, self.sim_count)
-        x = state[:, 3:6]
+        err = self._mc[algo_index]['end_err']
+        if dist.world() > 1:
+            import torch as _t
+            err = dist.gather_rows(_t.from_numpy(err), self.sim_count)
         r = self._traj['ref_pos'][-1]
+        x = err[:, 3:6] + r            # end position = error + truth
         err = lla2ecef(x) - lla2ecef(r)[0]
         if opt == 'ned':
             err = err.dot(ecef_to_ned(r[0], r[1]).T)
