@@ -521,7 +521,7 @@ int b2ins_mc_plan_create(int64_t n, int64_t max_runs, int ini_sets, int ini_rows
 }
 
 int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const double* ref_gyro,
-                      const double* ref_accel, const double* ref_nav, const double* ini,
+                      const double* ref_accel, const double* ref_nav_end, const double* ini,
                       double* end_err, double* stats) {
   ARG_CHECK(plan && cfg, "null plan / cfg");
   ARG_CHECK(cfg->n == plan->n && cfg->runs >= 1 && cfg->runs <= plan->max_runs &&
@@ -529,7 +529,7 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const dou
             "cfg does not fit the plan (n=%lld runs<=%lld ini=[%d][%d])",
             static_cast<long long>(plan->n), static_cast<long long>(plan->max_runs), plan->ini_sets,
             plan->ini_rows);
-  ARG_CHECK(ref_gyro && ref_accel && ref_nav && ini && stats, "null buffer");
+  ARG_CHECK(ref_gyro && ref_accel && ref_nav_end && ini && stats, "null buffer");
   ARG_CHECK(cfg->stats_start < 0 && cfg->dump_runs == 0,
             "a plan computes end-point errors and their statistics only");
   const int64_t n = plan->n;
@@ -539,7 +539,7 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const dou
   const size_t n3p = plan->n3p();
   std::memcpy(plan->h_in, ref_gyro, n3 * sizeof(double));
   std::memcpy(plan->h_in + n3p, ref_accel, n3 * sizeof(double));
-  std::memcpy(plan->h_in + 2 * n3p, ref_nav + (n - 1) * 9, 9 * sizeof(double));
+  std::memcpy(plan->h_in + 2 * n3p, ref_nav_end, 9 * sizeof(double));
   std::memcpy(plan->h_in + 2 * n3p + 9, ini, ini_d * sizeof(double));
   double* d_gyro = plan->d_in;
   double* d_accel = plan->d_in + n3p;
@@ -725,5 +725,17 @@ int b2ins_diag_dfma_rate(double* dfma_per_s) {
   *dfma_per_s = static_cast<double>(blocks) * threads * iters * 8.0 / (best * 1e-3);
   return B2INS_OK;
 }
+
+#ifdef B2INS_PHASE_CLOCKS
+// tools only: cumulative warp-cycles in (tile wait, phase A noise, phase A incl. GM scan, phase B)
+int b2ins_diag_phase_clocks(unsigned long long* out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, g_phase_clocks, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_phase_clocks, z, sizeof(z));
+  }
+  return B2INS_OK;
+}
+#endif
 
 }  // extern "C"

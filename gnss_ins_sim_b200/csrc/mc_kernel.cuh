@@ -16,6 +16,17 @@
 
 namespace b2ins {
 
+// Optional phase clocks (tools only: -DB2INS_PHASE_CLOCKS builds libb2ins_prof.so)
+#ifdef B2INS_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clocks[8];
+#define B2_CLK(var) const long long var = clock64()
+#define B2_ACC(i, t0, t1) \
+  if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_clocks[i], static_cast<unsigned long long>((t1) - (t0)))
+#else
+#define B2_CLK(var)
+#define B2_ACC(i, t0, t1)
+#endif
+
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTile = 128;   // samples per shared-memory tile (multiple of 32)
@@ -274,10 +285,14 @@ mc_kernel(const __grid_constant__ McParams p) {
         mbar_wait(&sm.empty[sp], static_cast<uint32_t>(((tile - 1) / kStages) & 1));
         issue_tile<FED, PROC>(sm, p, tile - 1 + kStages, sp);
       }
+      B2_CLK(cw0);
       mbar_wait(&sm.full[s], parity);
+      B2_CLK(cw1);
+      B2_ACC(0, cw0, cw1);
     }
 
     for (int base = 0; base < cnt; base += G) {
+      B2_CLK(ca0);
       // ---------------- phase A: lane j prepares sample t0 + base + j --------------
       double mg[3], ma[3];  // the complete measurement of sample base + j
       const int tj = base + j;
@@ -305,6 +320,8 @@ mc_kernel(const __grid_constant__ McParams p) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) mg[c] = ma[c] = zg[c] = za[c] = 0.0;
         }
+        B2_CLK(ca1);
+        B2_ACC(1, ca0, ca1);
         // + drift: the GM state d[t] (pathgen.py:583-590) or drift*z[t] if tau = inf (:591-593)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -325,6 +342,8 @@ mc_kernel(const __grid_constant__ McParams p) {
         }
       }
 
+      B2_CLK(cb0);
+      B2_ACC(2, ca0, cb0);
       // ---------------- phase B: serial over the G samples of the block ------------
       double keep[9];  // lane k keeps the state after sample base+k (history output)
 #pragma unroll
@@ -378,6 +397,8 @@ mc_kernel(const __grid_constant__ McParams p) {
           }
         }
       }
+      B2_CLK(cb1);
+      B2_ACC(3, cb0, cb1);
       // ---------------- histories: lane j writes the state of sample base+j+1 ---------
       if (warp_dumps && dump && tj < cnt && p.out_att && t + 1 < p.n) {
         const int64_t o = run * p.osr + (t + 1) * p.ost;

@@ -172,21 +172,46 @@ def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetomete
 
 class LazyRuns(Mapping):
     """dict-like {key: (n,3) array} of per-run histories, materialised on first access by
-    re-running the requested runs with history output (deterministic Philox streams)."""
+    re-running the requested runs with history output (deterministic Philox streams).
+    Keys are the reference's: the run index for sensor data (prefix None), '<algo>_<run>' for
+    algorithm outputs.  Nothing is built per run until somebody asks (a Monte-Carlo
+    experiment with 10^5 runs must not spend its time making 10^5 Python strings)."""
 
-    def __init__(self, sim, name, keys, run_of_key):
-        self._sim, self._name, self._keys, self._run = sim, name, list(keys), dict(run_of_key)
+    def __init__(self, sim, name, count, prefix=None):
+        self._sim, self._name, self._count, self._prefix = sim, name, int(count), prefix
+
+    def _key(self, r):
+        return r if self._prefix is None else '%s_%d' % (self._prefix, r)
+
+    def _run_of(self, key):
+        if self._prefix is None:
+            r = key
+        else:
+            if not isinstance(key, str) or not key.startswith(self._prefix + '_'):
+                raise KeyError(key)
+            try:
+                r = int(key[len(self._prefix) + 1:])
+            except ValueError:
+                raise KeyError(key)
+        if not isinstance(r, (int, np.integer)) or not 0 <= r < self._count:
+            raise KeyError(key)
+        return int(r)
+
+    def __contains__(self, key):
+        try:
+            self._run_of(key)
+            return True
+        except KeyError:
+            return False
 
     def __iter__(self):
-        return iter(self._keys)
+        return (self._key(r) for r in range(self._count))
 
     def __len__(self):
-        return len(self._keys)
+        return self._count
 
     def __getitem__(self, key):
-        if key not in self._run:
-            raise KeyError(key)
-        return self._sim._history(self._name, self._run[key])
+        return self._sim._history(self._name, self._run_of(key))
 
 
 # ------------------------------------------------------------------ the facade --
@@ -273,9 +298,18 @@ class Sim(object):
         d['fs'], d['ref_frame'], d['time'] = self.fs[0], self.ref_frame, traj['time']
         d['ref_pos'], d['ref_vel'], d['ref_att_euler'] = traj['ref_pos'], traj['ref_vel'], traj['ref_att']
         d['ref_accel'], d['ref_gyro'] = traj['ref_accel'], traj['ref_gyro']
-        self._nav = np.ascontiguousarray(
-            np.concatenate([traj['ref_att'], traj['ref_pos'], traj['ref_vel']], axis=1))
+        self._nav_end = np.concatenate([traj['ref_att'][-1], traj['ref_pos'][-1], traj['ref_vel'][-1]])
+        self._nav_cache = None
         self._dev_cache = None
+
+    @property
+    def _nav(self):
+        """[n][9] att,pos,vel of the true trajectory (built on first use)."""
+        if self._nav_cache is None:
+            t = self._traj
+            self._nav_cache = np.ascontiguousarray(
+                np.concatenate([t['ref_att'], t['ref_pos'], t['ref_vel']], axis=1))
+        return self._nav_cache
 
     @property
     def _dev(self):
@@ -310,9 +344,8 @@ class Sim(object):
                 raise NotImplementedError('PSD vibration is not built yet (K5)')
         R = self.sim_count
         self._shard = dist.shard(R)
-        keys = list(range(R))
-        self.data['accel'] = LazyRuns(self, 'accel', keys, {k: k for k in keys})
-        self.data['gyro'] = LazyRuns(self, 'gyro', keys, {k: k for k in keys})
+        self.data['accel'] = LazyRuns(self, 'accel', R)
+        self.data['gyro'] = LazyRuns(self, 'gyro', R)
         if self.algo is not None:
             for i, a in enumerate(self.algo):
                 if isinstance(a, FreeIntegration):
@@ -347,7 +380,7 @@ class Sim(object):
             cfg = self._mc_config(i, hi - lo, lo)
             t = self._traj
             plan = engine.get_plan(cfg.n, cfg.runs, cfg.ini_sets, cfg.ini_rows)
-            err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav, algo.ini_sets)
+            err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav_end, algo.ini_sets)
             self._mc[i]['end_err'] = err
             self.err_stats[name] = stats
         else:
@@ -361,11 +394,9 @@ class Sim(object):
                                                        self.sim_count)
             self._mc[i]['end_err'] = res.end_err.cpu().numpy() if res is not None else np.zeros((0, 9))
         algo.run_times += self.sim_count
-        keys = ['%s_%d' % (name, k) for k in range(self.sim_count)]
-        run_of = {k: r for r, k in enumerate(keys)}
         for out in ('att_euler', 'pos', 'vel'):
             prev = self.data.get(out)
-            lazy = LazyRuns(self, (i, out), keys, run_of)
+            lazy = LazyRuns(self, (i, out), self.sim_count, prefix=name)
             if isinstance(prev, _Merged):
                 prev.add(lazy)
             elif isinstance(prev, LazyRuns) and prev._name[0] != i:
@@ -621,6 +652,6 @@ class _Merged(Mapping):
 
     def __getitem__(self, key):
         for p in self._parts:
-            if key in p._run:
+            if key in p:
                 return p[key]
         raise KeyError(key)

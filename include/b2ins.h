@@ -169,7 +169,8 @@ int b2ins_mc_free_integration_f64_host(const b2ins_mc_config* cfg,
  * A plan owns everything one experiment shape (n samples, up to `runs` runs, ini sets)
  * needs between calls: device buffers, pinned staging buffers and a stream.  plan_run is
  * b2ins_mc_free_integration_f64_host without the per-call allocations: stage the host
- * inputs into pinned memory, ONE H2D copy (true IMU samples, the last ref_nav row, ini),
+ * inputs into pinned memory, H2D copy (true IMU samples, ref_nav_end = the 9 values
+ * att,pos,vel of the true trajectory at sample n-1, ini),
  * K12, K3, ONE D2H copy (stats [3][9] and, if end_err != NULL, the [runs][9] end-point
  * errors), synchronise.  This is what Sim.run() calls on a single GPU.  A plan is bound to
  * the device current at creation and is not thread-safe (one plan per thread). */
@@ -177,7 +178,7 @@ typedef struct b2ins_mc_plan b2ins_mc_plan;
 int b2ins_mc_plan_create(int64_t n, int64_t max_runs, int ini_sets, int ini_rows,
                          b2ins_mc_plan** plan);
 int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg,
-                      const double* ref_gyro, const double* ref_accel, const double* ref_nav,
+                      const double* ref_gyro, const double* ref_accel, const double* ref_nav_end,
                       const double* ini, double* end_err, double* stats);
 int b2ins_mc_plan_destroy(b2ins_mc_plan* plan);
 
