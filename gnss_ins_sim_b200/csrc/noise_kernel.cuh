@@ -76,10 +76,8 @@ __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_c
     const bool live = t < p.n;
     double m[6], z[6];
     if (live) {
-      noisy_triad(p.accel, p.ref_accel + t * 3, static_cast<uint32_t>(t), kDrawAccel, 0, run_lo,
-                  run_hi, p.k0, p.k1, run, phase, m, z);
-      noisy_triad(p.gyro, p.ref_gyro + t * 3, static_cast<uint32_t>(t), kDrawGyro, 1, run_lo,
-                  run_hi, p.k0, p.k1, run, phase, m + 3, z + 3);
+      noisy_sample(p, p.ref_accel + t * 3, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo,
+                   run_hi, run, phase, m, m + 3, z, z + 3);
     } else {
 #pragma unroll
       for (int c = 0; c < 6; ++c) m[c] = z[c] = 0.0;

@@ -416,7 +416,10 @@ class Sim(object):
         name = self.algo_name(i)
         R = self.sim_count
         n = self._traj['ref_gyro'].shape[0]
-        block = max(1, min(R, int(2e9 // (n * 48)) or 1))
+        # runs per block: K1 materialises 48 B and K4 needs ~2 B of workspace per run-sample;
+        # use up to a third of the free device memory
+        free_b = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 2 ** 31
+        block = max(1, min(R, int(free_b / 3 // (n * 64)) or 1))
         tau_all, ada, adg = None, {}, {}
         for r0 in range(0, R, block):
             r1 = min(R, r0 + block)

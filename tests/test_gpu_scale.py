@@ -1,0 +1,134 @@
+"""GPU parity at BASELINE config-3 / config-4 sizes (n = 193 036 samples @200 Hz, ref_frame 0;
+Allan over millions of samples): the CUDA path against the plain-C oracle (oracle/oracle.c,
+itself pinned to the reference's golden vectors) on synthetic trajectories, plus
+size-independent properties."""
+import numpy as np
+import pytest
+
+import oracle_c
+import oracle_np as onp
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+LOW_G = {'b': np.zeros(3), 'b_drift': np.full(3, 10.0 * np.pi / 180 / 3600),
+         'b_corr': np.full(3, 100.0), 'arw': np.full(3, 0.75 * np.pi / 180 / 60)}
+LOW_A = {'b': np.zeros(3), 'b_drift': np.full(3, 2.0e-4), 'b_corr': np.full(3, 100.0),
+         'vrw': np.full(3, 0.05 / 60)}
+
+
+@pytest.fixture(scope='module')
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from gnss_ins_sim_b200 import engine
+    return engine
+
+
+def synthetic_drive(n, fs):
+    """A smooth, singularity-free 'drive': gentle turns and accelerations (true IMU output
+    only has to be an input series for parity; it need not come from path_gen)."""
+    t = np.arange(n) / fs
+    gyro = np.stack([0.01 * np.sin(0.11 * t), 0.008 * np.sin(0.07 * t + 1.0),
+                     0.05 * np.sin(0.013 * t)], axis=1)
+    accel = np.stack([0.3 * np.sin(0.05 * t), 0.2 * np.cos(0.03 * t),
+                      -9.794 + 0.05 * np.sin(0.2 * t)], axis=1)
+    ini = np.array([31.5 * np.pi / 180, 120.4 * np.pi / 180, 10.0, 5.0, 0.0, 0.0, 3.19, 0.01, -0.02])
+    nav_end = np.zeros(9)
+    nav_end[3:6] = ini[0:3]
+    return np.ascontiguousarray(gyro), np.ascontiguousarray(accel), ini, nav_end
+
+
+@pytest.mark.parametrize('lanes', [1, 8, 32])
+def test_config3_length_fused_mc_vs_c_oracle(eng, lanes):
+    n, fs, R, seed = 193036, 200.0, 5, 20240922
+    gyro, accel, ini, nav_end = synthetic_drive(n, fs)
+    nav = np.zeros((n, 9))
+    nav[-1] = nav_end
+    o_err, _ = oracle_c.mc_free_integration(0, fs, R, 7, gyro, accel, nav_end, LOW_G, LOW_A, seed,
+                                            ini[None], threads=0)
+    cfg = eng.make_mc_config(0, fs, n, R, seed, LOW_G, LOW_A, 1, 9, run_offset=7, lanes_per_run=lanes)
+    res = eng.mc_free_integration(cfg, eng.to_device(gyro), eng.to_device(accel), eng.to_device(nav),
+                                  eng.to_device(ini[None]))
+    err = res.end_err.cpu().numpy()
+    # contract: 1e-6 relative (scale 1 rad / 1 m/s; lat/lon errors are ~1e-4 rad here)
+    assert_close(err[:, 0:3], o_err[:, 0:3], 1e-6, 1.0, 'att')
+    assert_close(err[:, 6:9], o_err[:, 6:9], 1e-6, 1.0, 'vel')
+    assert_close(err[:, 5], o_err[:, 5], 1e-6, 1.0, 'alt')
+    assert_close(err[:, 3:5] * 6.4e6, o_err[:, 3:5] * 6.4e6, 1e-6, 1.0, 'lat/lon in metres')
+    # and what it really achieves after 1.9e5 steps
+    assert np.abs(err[:, 6:9] - o_err[:, 6:9]).max() < 1e-7
+    assert np.abs((err[:, 3:5] - o_err[:, 3:5]) * 6.4e6).max() < 1e-5
+
+
+def test_config3_length_fed_vs_c_oracle(eng):
+    """K2 with supplied noise at n = 193 036, ref_frame 0 and 1, histories compared at strides."""
+    n, fs, R = 193036, 200.0, 2
+    gyro, accel, ini, _ = synthetic_drive(n, fs)
+    g, a = oracle_c.imu_noise(fs, gyro, accel, LOW_G, LOW_A, 99, np.arange(R))
+    for rf in (0, 1):
+        o_att, o_pos, o_vel = oracle_c.free_integration(rf, fs, g, a, np.tile(ini, (R, 1)))
+        att, pos, vel = eng.free_integration(rf, fs, eng.to_device(g), eng.to_device(a),
+                                             eng.to_device(ini[None]), lanes_per_run=16)
+        sl = slice(None, None, 997)
+        assert np.abs(att.cpu().numpy()[:, sl] - o_att[:, sl]).max() < 1e-7
+        assert_close(vel.cpu().numpy()[:, sl], o_vel[:, sl], 1e-6, 1.0, 'vel')
+        scale = 1.0 if rf == 1 else 1.0 / 6.4e6
+        assert_close(pos.cpu().numpy()[:, sl], o_pos[:, sl], 1e-6, scale, 'pos')
+
+
+def test_k1_long_series_gm_carry(eng):
+    """The Gauss-Markov carry across 750+ tiles of the time-parallel generator."""
+    n, fs, R = 193036, 200.0, 3
+    gyro, accel, ini, _ = synthetic_drive(n, fs)
+    g, a = eng.imu_noise(fs, R, eng.to_device(gyro), eng.to_device(accel), LOW_G, LOW_A, 5, 11)
+    og, oa = oracle_c.imu_noise(fs, gyro, accel, LOW_G, LOW_A, 5, np.arange(11, 11 + R))
+    assert_close(g.cpu().numpy(), og, 1e-11, 1.0, 'gyro')
+    assert_close(a.cpu().numpy(), oa, 1e-11, 1.0, 'accel')
+
+
+def test_k4_allan_millions_of_samples(eng):
+    """Four decade levels, ragged length, a constant offset 10^4 times the noise."""
+    rng = np.random.RandomState(4)
+    n, fs = 2000003, 400.0
+    x = np.empty((2, n, 3))
+    for r in range(2):
+        for c in range(3):
+            x[r, :, c] = -9.79 + 1e-3 * rng.randn(n) + np.cumsum(1e-6 * rng.randn(n))
+    avar, tau = eng.allan(fs, eng.to_device(x), n, 6, inner=3, outer_stride=3 * n, sample_stride=3)
+    avar = avar.cpu().numpy().reshape(2, 3, -1)
+    assert avar.shape[2] == len(onp.allan_multipliers(n, fs)) == 49
+    for r in range(2):
+        for c in range(3):
+            o, t = oracle_c.allan_var(x[r, :, c], fs)
+            assert_close(avar[r, c], o, 1e-9, 0.0, 'avar')
+    assert_close(tau.cpu().numpy(), t, 1e-15, 0.0, 'tau')
+
+
+def test_large_ensemble_properties(eng):
+    """BASELINE-size ensembles without an oracle: (i) two disjoint halves of 2^16 runs have
+    statistically identical error statistics, (ii) end-point std grows like the white-noise
+    random walk predicts (velocity error std ~ vrw*sqrt(T) within 20 %)."""
+    n, fs = 2000, 100.0
+    t = np.arange(n) / fs
+    gyro = np.zeros((n, 3))
+    accel = np.zeros((n, 3))
+    ini = np.array([0.55, 2.09, 0.0, 0.0, 0.0, 0.0, 0.3, 0.0, 0.0, 9.8])   # gravity override
+    accel[:, 2] = -9.8
+    nav = np.zeros((n, 9))
+    nav[:, 0] = 0.3
+    nav[:, 3:6] = onp.lla2ecef(ini[0:3])
+    quiet_g = {'b': np.zeros(3), 'b_drift': np.zeros(3), 'b_corr': np.full(3, 100.0), 'arw': np.zeros(3)}
+    acc = {'b': np.zeros(3), 'b_drift': np.zeros(3), 'b_corr': np.full(3, 100.0),
+           'vrw': np.full(3, 0.05 / 60)}
+    dev = [eng.to_device(a) for a in (gyro, accel, nav, ini[None])]
+    st = []
+    for off in (0, 65536):
+        cfg = eng.make_mc_config(1, fs, n, 65536, 77, quiet_g, acc, 1, 10, run_offset=off)
+        st.append(eng.error_stats(eng.mc_free_integration(cfg, *dev).end_err).cpu().numpy())
+    a, b = st
+    assert (np.abs(a[2, 6:9] / b[2, 6:9] - 1) < 0.03).all()
+    expect = 0.05 / 60 * np.sqrt(n / fs)            # vrw * sqrt(T)
+    assert (np.abs(a[2, 6:9] / expect - 1) < 0.2).all()
+    assert (np.abs(a[1, 6:9]) < 5 * a[2, 6:9] / np.sqrt(65536)).all()
