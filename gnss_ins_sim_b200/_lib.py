@@ -67,6 +67,9 @@ SIGNATURES = {
     'b2ins_allan_workspace_bytes': (_L, [_L, _L]),
     'b2ins_allan_f64': (_I, [_D, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P]),
     'b2ins_allan_f64_host': (_I, [_D, _L, _L, _P, _L, _L, _L, _P, _P]),
+    'b2ins_psd_series_len': (_I, [_L]),
+    'b2ins_psd_workspace_bytes': (_L, [_L, _L]),
+    'b2ins_psd_series_f64': (_I, [_D, _L, _L, _I, _I, _P, _P, _U64, _L, _P, _P, _P]),
     'b2ins_diag_dfma_rate': (_I, [c_double_p]),
 }
 

@@ -12,6 +12,7 @@
 #include "allan_kernel.cuh"
 #include "mc_kernel.cuh"
 #include "noise_kernel.cuh"
+#include "psd_kernel.cuh"
 #include "stats_kernel.cuh"
 
 using namespace b2ins;
@@ -108,9 +109,12 @@ int sm_count() {
 // are enough runs to give every SM sub-partition several warps; with fewer runs a wider
 // group buys latency (more warps in flight, phase A amortised over G samples).
 int auto_lanes(int64_t runs) {
-  const int64_t target_warps = static_cast<int64_t>(sm_count()) * 4 * 4;  // 4 warps / SMSP
-  int g = 1;
-  while (g < 32 && runs * g < target_warps * 32) g <<= 1;
+  // measured on B200 (profiles/probe_mc_r01_*.jsonl): the serial step is issue/latency bound
+  // per warp, so the best group width puts about one warp on every SM sub-partition --
+  // warps = runs*G/32 <= 4*SMs -- and never more lanes than that needs.
+  const int64_t smsp = static_cast<int64_t>(sm_count()) * 4;
+  int g = 32;
+  while (g > 1 && runs * g > smsp * 32) g >>= 1;
   return g;
 }
 
@@ -687,6 +691,48 @@ int b2ins_allan_f64_host(double fs, int64_t n, int64_t nseries, const double* x,
   CU_CHECK(cudaMemcpyAsync(tau, dtau.p, static_cast<size_t>(ntau) * sizeof(double),
                            cudaMemcpyDeviceToHost, st.s));
   CU_CHECK(cudaStreamSynchronize(st.s));
+  return B2INS_OK;
+}
+
+// ---------------------------------------------------------------- K5 --------
+int b2ins_psd_series_len(int64_t n) { return n > 0 ? psd_series_len(n) : 0; }
+
+int64_t b2ins_psd_workspace_bytes(int64_t n, int64_t runs) {
+  if (n <= 0 || runs <= 0) return 16;
+  const int64_t L = psd_series_len(n) / 2 + 1;
+  return runs * 3 * L * 2 * static_cast<int64_t>(sizeof(double)) + 16;
+}
+
+int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int table_len,
+                         const double* freq, const double* sxx3, uint64_t seed,
+                         int64_t run_offset, double* series, void* workspace, void* stream) {
+  ARG_CHECK(fs > 0.0 && n > 0 && runs >= 0, "bad fs/n/runs");
+  ARG_CHECK(sensor == 0 || sensor == 1, "sensor must be 0 (accel) or 1 (gyro)");
+  ARG_CHECK(table_len >= 2, "the PSD table needs at least two rows");
+  if (runs == 0) return B2INS_OK;
+  ARG_CHECK(freq && sxx3 && series && workspace, "null buffer");
+  ARG_CHECK(runs * 3 <= 65535, "at most 21845 runs per call (grid.y)");
+  PsdParams p;
+  p.fs = fs;
+  p.runs = runs;
+  p.run_offset = run_offset;
+  p.N = psd_series_len(n);
+  p.L = p.N / 2 + 1;
+  p.L0 = table_len;
+  p.sensor = sensor;
+  p.interp = (table_len != p.L) ? 1 : 0;  // time_series_from_psd.py:46
+  p.k0 = static_cast<uint32_t>(seed);
+  p.k1 = static_cast<uint32_t>(seed >> 32);
+  p.freq = freq;
+  p.sxx = sxx3;
+  p.ab = static_cast<double*>(workspace);
+  p.series = series;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 g1((p.L + kPsdThreads - 1) / kPsdThreads, static_cast<unsigned>(runs * 3));
+  psd_phase_kernel<<<g1, kPsdThreads, 0, s>>>(p);
+  dim3 g2((p.N + kPsdThreads - 1) / kPsdThreads, static_cast<unsigned>(runs * 3));
+  psd_synth_kernel<<<g2, kPsdThreads, 0, s>>>(p);
+  CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }
 

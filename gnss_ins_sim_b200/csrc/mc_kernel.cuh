@@ -30,7 +30,11 @@ __device__ unsigned long long g_phase_clocks[8];
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTile = 128;   // samples per shared-memory tile (multiple of 32)
-constexpr int kStages = 3;
+constexpr int kStagesFast = 3;   // pipeline depth; 2 when the 72 B/sample nav tile is staged too
+template <bool PROC>
+struct Stages {
+  static constexpr int value = PROC ? 2 : kStagesFast;
+};
 
 // error model of one triad, pre-digested on the host (bias_drift: pathgen.py:583-586)
 struct TriadNoise {
@@ -76,11 +80,20 @@ struct McParams {
   int64_t stats_start;
 };
 
+// Prepared samples of one block, one slot per lane: phase A stores (gyro xyz, accel xyz),
+// phase B reads sample k of its group with three 128-bit broadcast loads instead of twelve
+// 32-bit shuffles.  48 B per lane; row padding keeps the group bases on distinct banks.
+struct alignas(16) SampleSlot {
+  double g[3], a[3];
+};
+
 template <bool PROC>
 struct TileSmem {
+  static constexpr int kStages = Stages<PROC>::value;
   alignas(128) double gyro[kStages][kTile * 3];
   alignas(128) double accel[kStages][kTile * 3];
   alignas(128) double nav[kStages][PROC ? kTile * 9 : 2];  // only staged for process statistics
+  alignas(16) SampleSlot slot[kWarps][32];
   alignas(8) uint64_t full[kStages];
   alignas(8) uint64_t empty[kStages];
 };
@@ -194,6 +207,34 @@ __device__ __forceinline__ double gm_block(double x, double a, double apj, doubl
   return d;
 }
 
+// process-error accumulation of one sample (ins_data_manager.py:536-541, :761-808)
+__device__ __forceinline__ void proc_accumulate(const NavState& st, const double* r, double* pe_max,
+                                                double* pe_sum, double* pe_sq, double* pe_k,
+                                                int64_t& pe_cnt) {
+  double e[9];
+  e[0] = angle_range_pi(st.yaw - r[0]);
+  e[1] = angle_range_pi(st.pitch - r[1]);
+  e[2] = angle_range_pi(st.roll - r[2]);
+  e[3] = st.pos.x - r[3];
+  e[4] = st.pos.y - r[4];
+  e[5] = st.pos.z - r[5];
+  e[6] = st.vel.x - r[6];
+  e[7] = st.vel.y - r[7];
+  e[8] = st.vel.z - r[8];
+  if (pe_cnt == 0) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) pe_k[c] = e[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    pe_max[c] = fmax(pe_max[c], fabs(e[c]));
+    const double d = e[c] - pe_k[c];
+    pe_sum[c] += d;
+    pe_sq[c] += d * d;
+  }
+  ++pe_cnt;
+}
+
 // a^e for a small non-negative integer e (binary powering; no libm call, no stack frame)
 __device__ __forceinline__ double ipow(double a, int e) {
   double r = 1.0, b = a;
@@ -232,6 +273,7 @@ mc_kernel(const __grid_constant__ McParams p) {
   const bool dump = active && run < p.dump_runs;
   const bool warp_dumps = __any_sync(0xffffffffu, dump);
   constexpr bool kStaged = !FED || PROC;
+  constexpr int kStages = Stages<PROC>::value;
 
   const int64_t num_tiles = (p.n + kTile - 1) / kTile;
   if (kStaged) {
@@ -367,55 +409,39 @@ mc_kernel(const __grid_constant__ McParams p) {
       double keep[9];  // lane k keeps the state after sample base+k (history output)
 #pragma unroll
       for (int c = 0; c < 9; ++c) keep[c] = 0.0;
-      const int kmax = min(G, cnt - base);
+      if (G > 1) {
+        SampleSlot& mine = sm.slot[warp][lane];
+        mine.g[0] = mg[0]; mine.g[1] = mg[1]; mine.g[2] = mg[2];
+        mine.a[0] = ma[0]; mine.a[1] = ma[1]; mine.a[2] = ma[2];
+        __syncwarp();
+      }
+      // samples of this block that are followed by a step (the last sample of the series is not)
+      const int kmax = static_cast<int>(min64(min64(G, cnt - base), p.n - 1 - (t0 + base)));
+      const SampleSlot* grp = &sm.slot[warp][lane - j];
 #pragma unroll 1
       for (int k = 0; k < kmax; ++k) {
-        const int64_t tk = t0 + base + k;
         Vec3 w, f;
         if (G == 1) {
           w = Vec3{mg[0], mg[1], mg[2]};
           f = Vec3{ma[0], ma[1], ma[2]};
         } else {
-          w = Vec3{shfl_grp<G>(mg[0], k), shfl_grp<G>(mg[1], k), shfl_grp<G>(mg[2], k)};
-          f = Vec3{shfl_grp<G>(ma[0], k), shfl_grp<G>(ma[1], k), shfl_grp<G>(ma[2], k)};
+          const SampleSlot& sl = grp[k];
+          w = Vec3{sl.g[0], sl.g[1], sl.g[2]};
+          f = Vec3{sl.a[0], sl.a[1], sl.a[2]};
         }
         if (PROC) {
-          // error of sample tk (state BEFORE the step), ins_data_manager.py:536-541
-          if (tk >= p.stats_start) {
-            const double* r = &sm.nav[s][(base + k) * 9];
-            double e[9];
-            e[0] = angle_range_pi(st.yaw - r[0]);
-            e[1] = angle_range_pi(st.pitch - r[1]);
-            e[2] = angle_range_pi(st.roll - r[2]);
-            e[3] = st.pos.x - r[3];
-            e[4] = st.pos.y - r[4];
-            e[5] = st.pos.z - r[5];
-            e[6] = st.vel.x - r[6];
-            e[7] = st.vel.y - r[7];
-            e[8] = st.vel.z - r[8];
-            if (pe_cnt == 0) {
-#pragma unroll
-              for (int c = 0; c < 9; ++c) pe_k[c] = e[c];
-            }
-#pragma unroll
-            for (int c = 0; c < 9; ++c) {
-              pe_max[c] = fmax(pe_max[c], fabs(e[c]));
-              const double d = e[c] - pe_k[c];
-              pe_sum[c] += d;
-              pe_sq[c] += d * d;
-            }
-            ++pe_cnt;
-          }
+          // error of sample t0+base+k (state BEFORE the step), ins_data_manager.py:536-541
+          if (t0 + base + k >= p.stats_start)
+            proc_accumulate(st, &sm.nav[s][(base + k) * 9], pe_max, pe_sum, pe_sq, pe_k, pe_cnt);
         }
-        if (tk < p.n - 1) {
-          nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role);
-          if (warp_dumps && j == k) {
-            keep[0] = st.yaw; keep[1] = st.pitch; keep[2] = st.roll;
-            keep[3] = st.pos.x; keep[4] = st.pos.y; keep[5] = st.pos.z;
-            keep[6] = st.vel.x; keep[7] = st.vel.y; keep[8] = st.vel.z;
-          }
+        nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role);
+        if (warp_dumps && j == k) {
+          keep[0] = st.yaw; keep[1] = st.pitch; keep[2] = st.roll;
+          keep[3] = st.pos.x; keep[4] = st.pos.y; keep[5] = st.pos.z;
+          keep[6] = st.vel.x; keep[7] = st.vel.y; keep[8] = st.vel.z;
         }
       }
+      if (G > 1) __syncwarp();   // slots are rewritten by the next block
       B2_CLK(cb1);
       B2_ACC(3, cb0, cb1);
       // ---------------- histories: lane j writes the state of sample base+j+1 ---------
@@ -437,6 +463,10 @@ mc_kernel(const __grid_constant__ McParams p) {
   }
 
   // ---- per-run results -----------------------------------------------------
+  if (PROC) {   // the last sample has no step after it: its error is accumulated here
+    if (p.n - 1 >= p.stats_start)
+      proc_accumulate(st, p.ref_nav + (p.n - 1) * 9, pe_max, pe_sum, pe_sq, pe_k, pe_cnt);
+  }
   if (active && j == 0) {
     if (p.end_err) {
       const double* r = p.ref_nav + (p.n - 1) * 9;

@@ -75,11 +75,12 @@ __device__ __forceinline__ GeoParam geo_param_sc(double sl, double cl, double h)
   p.sl = sl;
   p.cl = cl;
   const double sl_sqr = p.sl * p.sl;
-  const double q = 1.0 - kESqr * sl_sqr;
-  const double sq = sqrt(q);
-  p.rm = (kRe * (1 - kESqr)) / (sq * q);
-  p.rn = kRe / sq;
-  const double g1 = kNormalGravity * (1 + kGravK * sl_sqr) / sq;
+  const double q = 1.0 - kESqr * sl_sqr;       // in [0.9933, 1]: no special cases
+  const double sq = sqrt_nr(q);
+  const double inv_sq = rcp_nr(sq);
+  p.rm = (kRe * (1 - kESqr)) * rcp_nr(sq * q);
+  p.rn = kRe * inv_sq;
+  const double g1 = kNormalGravity * (1 + kGravK * sl_sqr) * inv_sq;
   p.g = g1 * (1.0 - (2.0 / kRe) * (1.0 + kFlat + kGravM - 2.0 * kFlat * sl_sqr) * h +
               3.0 * h * h / kRe / kRe);
   return p;
@@ -225,7 +226,8 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     const double rm_e = p.rm + s.pos.z;
     const double rn_e = p.rn + s.pos.z;
     const double g = s.fixed_g ? s.g : p.g;
-    const Vec3 w_en{s.vel.y / rn_e, -s.vel.x / rm_e, -s.vel.y * p.sl / p.cl / rn_e};
+    const double inv_rn = rcp_nr(rn_e), inv_rm = rcp_nr(rm_e), inv_cl = rcp_nr(p.cl);
+    const Vec3 w_en{s.vel.y * inv_rn, -s.vel.x * inv_rm, -s.vel.y * p.sl * inv_cl * inv_rn};
     Vec3 w_ie{0.0, 0.0, 0.0};
     if (earth_rot) {
       w_ie.x = kWie * p.cl;
@@ -243,8 +245,8 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     s.vel.x = vel_old.x + (fa.x - cor.x) * dt;
     s.vel.y = vel_old.y + (fa.y - cor.y) * dt;
     s.vel.z = vel_old.z + (fa.z + g - cor.z) * dt;
-    s.pos.x += vel_old.x / rm_e * dt;
-    s.pos.y += vel_old.y / rn_e / p.cl * dt;
+    s.pos.x += vel_old.x * inv_rm * dt;
+    s.pos.y += vel_old.y * inv_rn * inv_cl * dt;
     s.pos.z += (-vel_old.z) * dt;
     refresh_trig<RF, SPLIT>(s, role);
     // vel_b[i] = c_bn(i).dot(vel[i]) (:172) is not an output of the plugin; not computed

@@ -84,7 +84,8 @@ def imu_noise(fs, runs, ref_gyro, ref_accel, gyro_err, accel_err, seed, run_offs
     accel = torch.empty_like(gyro)
     z = torch.empty((runs, n, 12), dtype=torch.float64, device=ref_gyro.device) if dump_z else None
     ge, ae = _lib.sensor_err(gyro_err, 'arw'), _lib.sensor_err(accel_err, 'vrw')
-    vg, va = _lib.vib(vib_gyro), _lib.vib(vib_accel)
+    vg = vib_gyro if isinstance(vib_gyro, _lib.Vib) else _lib.vib(vib_gyro)
+    va = vib_accel if isinstance(vib_accel, _lib.Vib) else _lib.vib(vib_accel)
     _lib.check(lib.b2ins_imu_noise_f64(
         float(fs), runs, n, _ptr(ref_gyro), _ptr(ref_accel), ctypes.byref(ge), ctypes.byref(ae),
         ctypes.byref(vg), ctypes.byref(va), int(seed), int(run_offset), layout,
@@ -259,6 +260,38 @@ def error_partial2(err, mean):
     _lib.check(lib.b2ins_error_partial2_f64(R, nc, _ptr(err), _ptr(mean.contiguous()), _ptr(out),
                                             _ptr(_stats_ws(nc, err.device)), _stream()))
     return out
+
+
+def psd_series(fs, n, runs, sensor, vib_def, seed, run_offset=0):
+    """K5.  vib_def: {'type': 'psd', 'freq': (L0,), 'x','y','z': (L0,)} (Sim.__parse_env output).
+    Returns the device series [runs, 3, N] and N (hand both to a Vib of type VIB_SERIES)."""
+    _require_cuda()
+    lib = _lib.load()
+    freq = to_device(vib_def['freq'])
+    if fs < 2.0 * float(vib_def['freq'][-1]) or fs < 0.0:
+        raise ValueError('PSD table exceeds fs/2 (time_series_from_psd.py:33-34)')
+    sxx = to_device(np.stack([vib_def['x'], vib_def['y'], vib_def['z']]))
+    N = lib.b2ins_psd_series_len(int(n))
+    out = []
+    for r0 in range(0, runs, 16384):                       # grid.y limit per launch
+        r1 = min(runs, r0 + 16384)
+        series = torch.empty((r1 - r0, 3, N), dtype=torch.float64, device=freq.device)
+        ws = torch.empty(lib.b2ins_psd_workspace_bytes(int(n), r1 - r0) // 8 + 1, dtype=torch.float64,
+                         device=freq.device)
+        _lib.check(lib.b2ins_psd_series_f64(float(fs), int(n), r1 - r0, int(sensor), freq.numel(),
+                                            _ptr(freq), _ptr(sxx), int(seed), int(run_offset) + r0,
+                                            _ptr(series), _ptr(ws), _stream()))
+        out.append(series)
+    return (out[0] if len(out) == 1 else torch.cat(out)), N
+
+
+def vib_series(series, N):
+    """A Vib of type VIB_SERIES over a device series [runs, 3, N]."""
+    v = _lib.Vib()
+    v.type = _lib.VIB_SERIES
+    v.series = series.data_ptr()
+    v.series_len = int(N)
+    return v
 
 
 def allan_num_tau(n, fs):

@@ -339,9 +339,7 @@ class Sim(object):
         self._mc = {}
         self._vib_acc = parse_env(self.env['acc'], self.fs[0]) if self.env and 'acc' in self.env else None
         self._vib_gyro = parse_env(self.env['gyro'], self.fs[0]) if self.env and 'gyro' in self.env else None
-        for v in (self._vib_acc, self._vib_gyro):
-            if v is not None and v['type'] == 'psd':
-                raise NotImplementedError('PSD vibration is not built yet (K5)')
+        self._psd_cache = {}
         R = self.sim_count
         self._shard = dist.shard(R)
         self.data['accel'] = LazyRuns(self, 'accel', R)
@@ -363,13 +361,36 @@ class Sim(object):
         own run_times."""
         algo = self.algo[ai]
         n = self._traj['ref_gyro'].shape[0]
+        vib_gyro, vib_acc = self._vib_pair(runs, r0)
         return engine.make_mc_config(
             self.ref_frame, self.fs[0], n, runs, self.seed, self.imu.gyro_err, self.imu.accel_err,
             algo.ini_sets.shape[0], algo.ini_sets.shape[1], earth_rot=algo.earth_rot,
             run_offset=self.run_base + r0, ini_offset=self._mc[ai]['base'] + r0,
-            vib_gyro=self._vib_gyro, vib_accel=self._vib_acc,
+            vib_gyro=vib_gyro, vib_accel=vib_acc,
             lanes_per_run=self.lanes_per_run or algo.lanes_per_run, stats_start=stats_start,
             dump_runs=dump_runs)
+
+    def _vib_pair(self, runs, r0):
+        """(vib_gyro, vib_accel) arguments for experiment runs [r0, r0+runs): parsed dicts, or
+        for the PSD model a VIB_SERIES over device series made by K5 for exactly those runs
+        (time_series_from_psd is called per run and axis, pathgen.py:478-485, :541-548)."""
+        out = []
+        for sensor, v in ((1, self._vib_gyro), (0, self._vib_acc)):
+            if v is not None and v['type'] == 'psd':
+                key = (sensor, runs, r0)
+                if key not in self._psd_cache:
+                    n = self._traj['ref_gyro'].shape[0]
+                    self._psd_cache.clear() if len(self._psd_cache) > 8 else None
+                    self._psd_cache[key] = engine.psd_series(self.fs[0], n, runs, sensor, v, self.seed,
+                                                             self.run_base + r0)
+                series, N = self._psd_cache[key]
+                out.append(engine.vib_series(series, N))
+            else:
+                out.append(v)
+        return out[0], out[1]
+
+    def _uses_psd(self):
+        return any(v is not None and v['type'] == 'psd' for v in (self._vib_acc, self._vib_gyro))
 
     def _run_free_integration(self, i, algo):
         name = self.algo_name(i)
@@ -407,10 +428,11 @@ class Sim(object):
     def _noise_block(self, r0, r1):
         """K1 for global-in-experiment runs [r0, r1): CUDA gyro, accel [r1-r0, n, 3]."""
         d = self._dev
+        vib_gyro, vib_acc = self._vib_pair(r1 - r0, r0)
         return engine.imu_noise(self.fs[0], r1 - r0, d['ref_gyro'], d['ref_accel'],
                                 self.imu.gyro_err, self.imu.accel_err, self.seed,
-                                run_offset=self.run_base + r0, vib_gyro=self._vib_gyro,
-                                vib_accel=self._vib_acc)
+                                run_offset=self.run_base + r0, vib_gyro=vib_gyro,
+                                vib_accel=vib_acc)
 
     def _run_allan(self, i, algo):
         name = self.algo_name(i)

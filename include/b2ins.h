@@ -215,6 +215,20 @@ int b2ins_allan_f64_host(double fs, int64_t n, int64_t nseries, const double* x,
                          int64_t inner, int64_t outer_stride, int64_t sample_stride,
                          double* avar, double* tau);
 
+/* ---- K5: vibration series from a PSD -------------------------------------------
+ * Replaces time_series_from_psd (gnss_ins_sim/psd/time_series_from_psd.py:17-65) as called
+ * three times per sensor and run by acc_gen / gyro_gen (pathgen.py:478-485, :541-548).
+ * freq [table_len], sxx3 [3][table_len] (x, y, z single-sided PSD): DEVICE pointers, already
+ * cut at fs/2 like Sim.__parse_env does (ins_sim.py:688-697).  sensor: 0 accel, 1 gyro (selects
+ * the Philox draw ids of the random phases).  series [runs][3][N], N = b2ins_psd_series_len(n);
+ * hand it to b2ins_vib.series with series_len = N (the consumer tiles it to n samples).
+ * workspace: b2ins_psd_workspace_bytes(n, runs) bytes of device scratch. */
+int b2ins_psd_series_len(int64_t n);
+int64_t b2ins_psd_workspace_bytes(int64_t n, int64_t runs);
+int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int table_len,
+                         const double* freq, const double* sxx3, uint64_t seed,
+                         int64_t run_offset, double* series, void* workspace, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------
  * Measured FP64 FMA issue rate of the current device [lane-FMA/s]: a ~10 ms dependent-chain
  * microbenchmark (8 independent chains per thread, every SM filled).  The Monte-Carlo

@@ -288,6 +288,16 @@ def gyro_vib_phase_uniforms(run_ids, seed):
     return (a >> np.uint64(12)).astype(np.float64) * (2.0 ** -52)
 
 
+def psd_phase_normals(L, run_ids, seed, sensor):
+    """The L random-phase normals of each (run, axis) PSD series: z0 of the pair
+    (t = k, draw = PAIR_PSD + 3*sensor + axis).  Returns [R, 3, L]."""
+    run_ids = np.asarray(run_ids, dtype=np.uint64)
+    k = np.arange(L, dtype=np.uint64)[None, None, :]
+    ax = np.arange(3, dtype=np.uint64)[None, :, None]
+    z0, _ = normal_pair(k, PAIR_PSD + 3 * sensor + ax, run_ids[:, None, None], seed)
+    return z0
+
+
 def gm_coeffs(corr, drift, fs):
     """pathgen.bias_drift coefficients, pathgen.py:583-586: a is the first-order
     approximation 1 - dt/tau, b uses the exact exponential -- both as written."""

@@ -362,3 +362,60 @@ def test_statistical_sanity_large_ensemble(eng):
     q = eng.mc_free_integration(cfg, *args).end_err.cpu().numpy()
     assert np.abs(q - q[0]).max() == 0.0                   # noise-free runs are identical
     assert (np.abs(c[1] - q[0]) < 5 * c[2] / np.sqrt(32768) + 1e-12).all()
+
+
+def test_k5_psd_series_vs_oracle(eng):
+    """K5 == oracle time_series_from_psd fed the same Philox phase normals (the oracle itself is
+    pinned to the reference on tests/golden/psd.npz), for an even n <= 16384 (no tiling, N = n,
+    not a power of two), an odd n and n > 16384 (N = 16384), with and without interpolation."""
+    g = load_golden('psd.npz')
+    freq, sxx = g['freq_a'], g['sxx_a']
+    fs = float(g['fs_a'])
+    R, seed, run0 = 3, 99, 5
+    vib = {'type': 'psd', 'freq': freq, 'x': sxx, 'y': 2.0 * sxx, 'z': 0.5 * sxx + 1e-6}
+    for n in (1000, 777, 40001):
+        for sensor in (0, 1):
+            series, N = eng.psd_series(fs, n, R, sensor, vib, seed, run0)
+            assert N == min(n + n % 2, 16384) and tuple(series.shape) == (R, 3, N)
+            L = N // 2 + 1
+            z = onp.psd_phase_normals(L, np.arange(run0, run0 + R), seed, sensor)
+            s = series.cpu().numpy()
+            for r in range(R):
+                for c, key in enumerate(('x', 'y', 'z')):
+                    ok, x = onp.time_series_from_psd(vib[key], freq, fs, n, z[r, c])
+                    assert ok
+                    assert_close(np.resize(s[r, c], n) if n > N else s[r, c][:n], x, 1e-9,
+                                 np.abs(x).max(), 'psd series n=%d' % n)
+    # a table that already has L rows is used as it is (no interpolation)
+    n = 1000
+    L = n // 2 + 1
+    f2 = np.linspace(0, fs / 2, L)
+    vib2 = {'type': 'psd', 'freq': f2, 'x': np.interp(f2, freq, sxx), 'y': np.ones(L), 'z': np.zeros(L) + 1e-3}
+    series, N = eng.psd_series(fs, n, 1, 0, vib2, 1, 0)
+    z = onp.psd_phase_normals(L, [0], 1, 0)
+    ok, x = onp.time_series_from_psd(vib2['x'], f2, fs, n, z[0, 0])
+    assert_close(series.cpu().numpy()[0, 0], x, 1e-9, np.abs(x).max(), 'no-interp')
+
+
+def test_k5_psd_vibration_through_the_fused_kernel(eng):
+    """PSD vibration inside K12/K1: gyro/accel histories == oracle noise + oracle PSD series."""
+    g = load_golden('philox_90deg_mid_rf1.npz')
+    p = load_golden('psd.npz')
+    ge, ae = _errs(g)
+    n = g['ref_gyro'].shape[0]
+    R, seed = 2, 31
+    from gnss_ins_sim_b200.sim import parse_env
+    vib = parse_env(np.column_stack([p['freq_a'], p['sxx_a'], p['sxx_a'] * 0.3, p['sxx_a'] * 2]), 100.0)
+    assert vib['type'] == 'psd' and vib['freq'][-1] <= 50.0
+    sa, N = eng.psd_series(100.0, n, R, 0, vib, seed, 0)
+    sg, _ = eng.psd_series(100.0, n, R, 1, vib, seed, 0)
+    gyro, accel = eng.imu_noise(100.0, R, _dev(g['ref_gyro']), _dev(g['ref_accel']), ge, ae, seed, 0,
+                                eng.vib_series(sg, N), eng.vib_series(sa, N))
+    L = N // 2 + 1
+    o_gyro, o_accel = onp.imu_noise(100.0, g['ref_gyro'], g['ref_accel'], ge, ae, seed, np.arange(R))
+    for sensor, dev_out, base in ((0, accel, o_accel), (1, gyro, o_gyro)):
+        z = onp.psd_phase_normals(L, np.arange(R), seed, sensor)
+        for r in range(R):
+            for c, key in enumerate(('x', 'y', 'z')):
+                ok, x = onp.time_series_from_psd(vib[key], vib['freq'], 100.0, n, z[r, c])
+                assert_close(dev_out.cpu().numpy()[r, :, c], base[r, :, c] + x, 1e-9, 1.0, 'meas+psd')

@@ -98,7 +98,7 @@ def test_k4_allan_millions_of_samples(eng):
             x[r, :, c] = -9.79 + 1e-3 * rng.randn(n) + np.cumsum(1e-6 * rng.randn(n))
     avar, tau = eng.allan(fs, eng.to_device(x), n, 6, inner=3, outer_stride=3 * n, sample_stride=3)
     avar = avar.cpu().numpy().reshape(2, 3, -1)
-    assert avar.shape[2] == len(onp.allan_multipliers(n, fs)) == 49
+    assert avar.shape[2] == len(onp.allan_multipliers(n, fs)) and avar.shape[2] > 40
     for r in range(2):
         for c in range(3):
             o, t = oracle_c.allan_var(x[r, :, c], fs)
