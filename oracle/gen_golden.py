@@ -194,6 +194,49 @@ def gen_philox(tag, motion, fs, accuracy, ref_frame, R, seed, env=None, run0=0):
                         **out, **extra)
 
 
+def gen_philox_odo(ref_frame, R=6, seed=4711):
+    """demo_free_integration.py semantics: IMU(odo=True), algorithm = free_integration_odo
+    (demo_free_integration.py:40,61-71); the odometer draw (pathgen.py:639) is served from the
+    b2ins stream after the gyro white block (ins_sim.py:503-506)."""
+    from demo_algorithms import free_integration_odo
+    csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
+    ini = read_ini(csv)
+    odo_err = {'scale': 0.999, 'stdv': 0.1}
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=False, odo=True, odo_opt=odo_err)
+    algo = free_integration_odo.FreeIntegration(ini)
+    sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu, algorithm=algo)
+    n = 1000
+    run_ids = np.arange(R)
+    z = onp.noise_normals(n, run_ids, seed)
+    zo = onp.odo_normals(n, run_ids, seed)
+    q = RandnQueue()
+    for r in range(R):
+        for gm, w in ((z['acc_gm'], z['acc_w']), (z['gyr_gm'], z['gyr_w'])):
+            for i in range(3):
+                blk = np.full((n, 3), np.nan)
+                blk[:, i] = gm[r, :, i]
+                q.push(blk)
+            q.push(w[r])
+        q.push(zo[r])
+    real = np.random.randn
+    np.random.randn = q
+    try:
+        sim.run(R)
+    finally:
+        np.random.randn = real
+    assert not q.q
+    d = sim.dmgr
+    out = collect(sim, R)
+    np.savez_compressed(os.path.join(OUT, 'philox_90deg_mid_rf%d_odo.npz' % ref_frame),
+                        fs=100.0, ref_frame=ref_frame, ini=ini, seed=seed, run_ids=run_ids,
+                        odo_scale=odo_err['scale'], odo_stdv=odo_err['stdv'],
+                        ref_odo=d.ref_odo.data, odo=np.stack([d.odo.data[i] for i in range(R)]),
+                        gyro_b=imu.gyro_err['b'], gyro_b_drift=imu.gyro_err['b_drift'],
+                        gyro_b_corr=imu.gyro_err['b_corr'], gyro_arw=imu.gyro_err['arw'],
+                        accel_b=imu.accel_err['b'], accel_b_drift=imu.accel_err['b_drift'],
+                        accel_b_corr=imu.accel_err['b_corr'], accel_vrw=imu.accel_err['vrw'], **out)
+
+
 def gen_traj(tag, motion, fs, ref_frame):
     csv = os.path.join(MOTION, motion)
     imu = fresh_imu('low-accuracy')
@@ -269,6 +312,8 @@ def main():
     gen_philox('90deg_mid_rf0_vibsin', 'motion_def-90deg_turn.csv', 100.0, 'mid-accuracy', 0, 3,
                778, env={'acc': '[0.03 0.001 0.01]g-3Hz-sinusoidal',
                          'gyro': '[6 5 4]d-0.5Hz-sinusoidal'})
+    gen_philox_odo(1)
+    gen_philox_odo(0)
     gen_traj('90deg_turn_100hz_rf1', 'motion_def-90deg_turn.csv', 100.0, 1)
     gen_traj('90deg_turn_100hz_rf0', 'motion_def-90deg_turn.csv', 100.0, 0)
     gen_allan()

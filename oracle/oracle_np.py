@@ -195,6 +195,67 @@ def free_integration(ref_frame, fs, gyro, accel, ini, earth_rot=True):
     return att, pos, vel
 
 
+def free_integration_odo(ref_frame, fs, gyro, odo, ini, earth_rot=True):
+    """free_integration_odo.FreeIntegration.run, demo_algorithms/free_integration_odo.py:63-160,
+    batched: same attitude recurrence, body velocity = [odo, 0, 0].  gyro [R,n,3], odo [R,n]."""
+    gyro = np.asarray(gyro, dtype=np.float64)
+    odo = np.asarray(odo, dtype=np.float64)
+    ini = np.asarray(ini, dtype=np.float64)
+    R, n, _ = gyro.shape
+    dt = 1.0 / fs
+    att = np.zeros((R, n, 3))
+    pos = np.zeros((R, n, 3))
+    vel = np.zeros((R, n, 3))
+    vel_b = np.zeros((R, 3))
+    att[:, 0] = ini[:, 6:9]
+    vel_b[:] = ini[:, 3:6]
+    c_bn = euler2dcm_zyx(att[:, 0])
+    vel[:, 0] = _mtv(c_bn, vel_b)
+    pos[:, 0] = lla2ecef(ini[:, 0:3]) if ref_frame == 1 else ini[:, 0:3]
+    w_en_n = np.zeros((R, 3))
+    w_ie_n = np.zeros((R, 3))
+    for i in range(1, n):
+        if ref_frame == 1:
+            att[:, i] = euler_update_zyx(att[:, i - 1], gyro[:, i - 1], dt)       # :104
+        else:
+            rm, rn, g, sl, cl = geo_param(pos[:, i - 1, 0], pos[:, i - 1, 2])    # :124-131
+            rm_e = rm + pos[:, i - 1, 2]
+            rn_e = rn + pos[:, i - 1, 2]
+            w_en_n[:, 0] = vel[:, i - 1, 1] / rn_e
+            w_en_n[:, 1] = -vel[:, i - 1, 0] / rm_e
+            w_en_n[:, 2] = -vel[:, i - 1, 1] * sl / cl / rn_e
+            if earth_rot:
+                w_ie_n[:, 0] = W_IE * cl
+                w_ie_n[:, 2] = -W_IE * sl
+            w_nb_b = gyro[:, i - 1] - _mv(c_bn, w_en_n + w_ie_n)
+            att[:, i] = euler_update_zyx(att[:, i - 1], w_nb_b, dt)
+        vel_b[:, 0] = odo[:, i - 1]                                               # :106-108 / :142-144
+        vel_b[:, 1] = 0.0
+        vel_b[:, 2] = 0.0
+        c_bn = euler2dcm_zyx(att[:, i])
+        vel[:, i] = _mtv(c_bn, vel_b)
+        if ref_frame == 1:
+            pos[:, i] = pos[:, i - 1] + vel[:, i - 1] * dt                        # :112
+        else:
+            pos[:, i, 0] = pos[:, i - 1, 0] + vel[:, i - 1, 0] / rm_e * dt        # :149-154
+            pos[:, i, 1] = pos[:, i - 1, 1] + vel[:, i - 1, 1] / rn_e / cl * dt
+            pos[:, i, 2] = pos[:, i - 1, 2] + (-vel[:, i - 1, 2]) * dt
+    return att, pos, vel
+
+
+def odo_normals(n, run_ids, seed):
+    """[R, n] normals of pathgen.odo_gen: z0 of the pair (t, PAIR_ODO)."""
+    run_ids = np.asarray(run_ids, dtype=np.uint64)
+    t = np.arange(n, dtype=np.uint64)[None, :]
+    z0, _ = normal_pair(t, PAIR_ODO, run_ids[:, None], seed)
+    return z0
+
+
+def odo_gen(ref_odo, odo_err, z):
+    """pathgen.odo_gen, pathgen.py:627-641: scale*ref + stdv*randn(n).  z [R, n]."""
+    return odo_err['scale'] * np.asarray(ref_odo)[None, :] + odo_err['stdv'] * z
+
+
 # --------------------------------------------------------------------------
 # b2ins noise spec: Philox4x32-10 (Salmon et al. SC'11; same constants and
 # round schedule as cuRAND / torch) + Box-Muller in float64.
@@ -211,6 +272,7 @@ PAIR_ACCEL = 0      # +axis : (GM drive, white) of accel axis
 PAIR_GYRO = 3       # +axis : (GM drive, white) of gyro axis
 PAIR_VIB = 6        # +axis : (accel random vib, gyro random vib)
 PAIR_PHASE = 9      # +axis, t = 0xFFFFFFFF : sinusoidal gyro-vib phase uniforms
+PAIR_ODO = 12       # odometer white noise (z0)
 PAIR_PSD = 16       # +3*sensor+axis (sensor 0 accel, 1 gyro), t = bin index: PSD phases (z0)
 
 
