@@ -35,7 +35,10 @@ class McConfig(ctypes.Structure):
                 ('vib_gyro', Vib), ('vib_accel', Vib),
                 ('ini_sets', ctypes.c_int32), ('ini_rows', ctypes.c_int32),
                 ('lanes_per_run', ctypes.c_int32), ('stats_start', ctypes.c_int32),
-                ('dump_runs', ctypes.c_int64)]
+                ('dump_runs', ctypes.c_int64),
+                ('algo', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('odo_scale', ctypes.c_double), ('odo_stdv', ctypes.c_double),
+                ('ref_odo', ctypes.c_void_p), ('dump_odo', ctypes.c_void_p)]
 
 
 class B2insError(RuntimeError):
@@ -52,6 +55,7 @@ SIGNATURES = {
     'b2ins_device_count': (_I, []),
     'b2ins_allan_num_tau': (_I, [_L, _D, c_int64_p, _I]),
     'b2ins_free_integration_f64': (_I, [_I, _D, _L, _L, _P, _P, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P]),
+    'b2ins_free_integration_odo_f64': (_I, [_I, _D, _L, _L, _P, _P, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P]),
     'b2ins_free_integration_f64_host': (_I, [_I, _D, _L, _L, _P, _P, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I]),
     'b2ins_imu_noise_f64': (_I, [_D, _L, _L, _P, _P, _SE, _SE, _VB, _VB, _U64, _L, _I, _P, _P, _P, _P]),
     'b2ins_imu_noise_f64_host': (_I, [_D, _L, _L, _P, _P, _SE, _SE, _VB, _VB, _U64, _L, _I, _P, _P, _P]),

@@ -215,11 +215,11 @@ int b2ins_allan_num_tau(int64_t n, double fs, int64_t* m, int m_cap) {
 }
 
 // ---------------------------------------------------------------- K2 --------
-int b2ins_free_integration_f64(int ref_frame, double fs, int64_t runs, int64_t n,
-                               const double* gyro, const double* accel, int layout,
-                               const double* ini, int ini_sets, int ini_rows, int64_t run_offset,
-                               int earth_rot, double* att, double* pos, double* vel,
-                               int lanes_per_run, void* stream) {
+static int free_integration_fed(int algo, int ref_frame, double fs, int64_t runs, int64_t n,
+                                const double* gyro, const double* accel, int layout,
+                                const double* ini, int ini_sets, int ini_rows, int64_t run_offset,
+                                int earth_rot, double* att, double* pos, double* vel,
+                                int lanes_per_run, void* stream) {
   ARG_CHECK(ref_frame == 0 || ref_frame == 1, "ref_frame must be 0 or 1, got %d", ref_frame);
   ARG_CHECK(fs > 0.0, "fs must be positive");
   ARG_CHECK(runs >= 0 && n >= 0, "runs and n must be non-negative");
@@ -242,6 +242,13 @@ int b2ins_free_integration_f64(int ref_frame, double fs, int64_t runs, int64_t n
   p.fed_gyro = gyro;
   p.fed_accel = accel;
   layout_strides(layout, runs, n, &p.sr, &p.st, &p.sc);
+  p.algo = algo;
+  if (algo == 1) {   // `accel` carries the odometer series [R][n] or [n][R]
+    p.fed_accel = nullptr;
+    p.fed_odo = accel;
+    p.so_r = (layout == B2INS_LAYOUT_RUN_MAJOR) ? n : 1;
+    p.so_t = (layout == B2INS_LAYOUT_RUN_MAJOR) ? 1 : runs;
+  }
   p.out_att = att;
   p.out_pos = pos;
   p.out_vel = vel;
@@ -258,6 +265,24 @@ int b2ins_free_integration_f64(int ref_frame, double fs, int64_t runs, int64_t n
     if (layout == B2INS_LAYOUT_RUN_MAJOR && lanes < 8) lanes = 8;
   }
   return launch_mc(p, lanes, ref_frame, true, false, static_cast<cudaStream_t>(stream));
+}
+
+int b2ins_free_integration_f64(int ref_frame, double fs, int64_t runs, int64_t n,
+                               const double* gyro, const double* accel, int layout,
+                               const double* ini, int ini_sets, int ini_rows, int64_t run_offset,
+                               int earth_rot, double* att, double* pos, double* vel,
+                               int lanes_per_run, void* stream) {
+  return free_integration_fed(0, ref_frame, fs, runs, n, gyro, accel, layout, ini, ini_sets,
+                              ini_rows, run_offset, earth_rot, att, pos, vel, lanes_per_run, stream);
+}
+
+int b2ins_free_integration_odo_f64(int ref_frame, double fs, int64_t runs, int64_t n,
+                                   const double* gyro, const double* odo, int layout,
+                                   const double* ini, int ini_sets, int ini_rows,
+                                   int64_t run_offset, int earth_rot, double* att, double* pos,
+                                   double* vel, int lanes_per_run, void* stream) {
+  return free_integration_fed(1, ref_frame, fs, runs, n, gyro, odo, layout, ini, ini_sets,
+                              ini_rows, run_offset, earth_rot, att, pos, vel, lanes_per_run, stream);
 }
 
 int b2ins_free_integration_f64_host(int ref_frame, double fs, int64_t runs, int64_t n,
@@ -419,6 +444,16 @@ int b2ins_mc_free_integration_f64(const b2ins_mc_config* cfg, const double* ref_
   p.end_state = end_state;
   p.proc_stats = proc_stats;
   p.stats_start = cfg->stats_start;
+  ARG_CHECK(cfg->algo == 0 || cfg->algo == 1, "algo must be 0 (free integration) or 1 (odometer)");
+  p.algo = cfg->algo;
+  if (cfg->algo == 1) {
+    ARG_CHECK(cfg->ref_odo, "algo 1 needs ref_odo");
+    p.ref_odo = cfg->ref_odo;
+    p.odo_scale = cfg->odo_scale;
+    p.odo_stdv = cfg->odo_stdv;
+    p.out_odo = cfg->dump_odo;
+    if (cfg->dump_odo && p.dump_runs == 0) p.dump_runs = cfg->dump_runs;
+  }
   const int lanes = cfg->lanes_per_run ? cfg->lanes_per_run : auto_lanes(cfg->runs);
   return launch_mc(p, lanes, cfg->ref_frame, false, cfg->stats_start >= 0,
                    static_cast<cudaStream_t>(stream));

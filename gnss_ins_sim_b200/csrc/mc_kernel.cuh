@@ -65,12 +65,19 @@ struct McParams {
   const double* fed_gyro;
   const double* fed_accel;
   int64_t sr, st, sc;
+  // odometer variant (free_integration_odo): algo = 1
+  int algo;
+  const double* ref_odo;   // [n] true forward speed (pathgen 'odo')
+  double odo_scale, odo_stdv;
+  const double* fed_odo;   // K2: element (r,t) at r*so_r + t*so_t
+  int64_t so_r, so_t;
   // histories for runs [0, dump_runs): same stride convention
   double* out_att;
   double* out_pos;
   double* out_vel;
   double* out_gyro;
   double* out_accel;
+  double* out_odo;     // [dump_runs][n] (algo 1)
   int64_t osr, ost, osc;
   int64_t dump_runs;
   // per-run results
@@ -272,6 +279,7 @@ mc_kernel(const __grid_constant__ McParams p) {
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
   const bool dump = active && run < p.dump_runs;
   const bool warp_dumps = __any_sync(0xffffffffu, dump);
+  const bool odo_mode = p.algo == 1;
   constexpr bool kStaged = !FED || PROC;
   constexpr int kStages = Stages<PROC>::value;
 
@@ -358,6 +366,7 @@ mc_kernel(const __grid_constant__ McParams p) {
       B2_CLK(ca0);
       // ---------------- phase A: lane j prepares sample t0 + base + j --------------
       double mg[3], ma[3];  // the complete measurement of sample base + j
+      double mo = 0.0;      // odometer measurement (algo 1)
       const int tj = base + j;
       const int64_t t = t0 + tj;
       if (FED) {
@@ -366,8 +375,9 @@ mc_kernel(const __grid_constant__ McParams p) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             mg[c] = p.fed_gyro[o + c * p.sc];
-            ma[c] = p.fed_accel[o + c * p.sc];
+            ma[c] = odo_mode ? 0.0 : p.fed_accel[o + c * p.sc];
           }
+          if (odo_mode) mo = p.fed_odo[run * p.so_r + t * p.so_t];
         } else {
 #pragma unroll
           for (int c = 0; c < 3; ++c) mg[c] = ma[c] = 0.0;
@@ -393,6 +403,11 @@ mc_kernel(const __grid_constant__ McParams p) {
           ma[c] += da + p.accel.wd[c] * za[c];
           mg[c] += dg + p.gyro.wd[c] * zg[c];
         }
+        if (odo_mode) {   // pathgen.odo_gen, pathgen.py:627-641: scale*ref + stdv*randn
+          const double zo = (tj < cnt) ? normal_pair(static_cast<uint32_t>(t), kDrawOdo, run_lo, run_hi,
+                                                     p.k0, p.k1).z0 : 0.0;
+          mo = (tj < cnt) ? p.odo_scale * p.ref_odo[t] + p.odo_stdv * zo : 0.0;
+        }
       }
       if (warp_dumps && dump && tj < cnt && p.out_gyro) {
         const int64_t o = run * p.osr + t * p.ost;
@@ -401,6 +416,11 @@ mc_kernel(const __grid_constant__ McParams p) {
           p.out_gyro[o + c * p.osc] = mg[c];
           p.out_accel[o + c * p.osc] = ma[c];
         }
+        if (odo_mode && p.out_odo) p.out_odo[run * p.n + t] = mo;
+      }
+      if (odo_mode) {   // the odometer sample rides to phase B in the accel.x slot
+        ma[0] = mo;
+        ma[1] = ma[2] = 0.0;
       }
 
       B2_CLK(cb0);
@@ -434,7 +454,7 @@ mc_kernel(const __grid_constant__ McParams p) {
           if (t0 + base + k >= p.stats_start)
             proc_accumulate(st, &sm.nav[s][(base + k) * 9], pe_max, pe_sum, pe_sq, pe_k, pe_cnt);
         }
-        nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role);
+        nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role, odo_mode);
         if (warp_dumps && j == k) {
           keep[0] = st.yaw; keep[1] = st.pitch; keep[2] = st.roll;
           keep[3] = st.pos.x; keep[4] = st.pos.y; keep[5] = st.pos.z;

@@ -201,9 +201,13 @@ __device__ __forceinline__ void euler_update(NavState& s, const Vec3& w, double 
 }
 
 // One step i-1 -> i with the measurements of sample i-1.
+//
+// odo = false: FreeIntegration.run (free_integration.py:104-116 / :133-172).
+// odo = true : free_integration_odo (free_integration_odo.py:104-112 / :121-158): same attitude
+//              recurrence, body velocity = [odometer, 0, 0]; the odometer sample rides in accel.x.
 template <int RF, bool SPLIT>
 __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel,
-                                         double dt, bool earth_rot, int role) {
+                                         double dt, bool earth_rot, int role, bool odo) {
   if (RF == 1) {
     // free_integration.py:104-116
     // c_bn.dot(g_n) with g_n = [0,0,g]: third column of the OLD dcm, from the old sin/cos
@@ -211,9 +215,13 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     const Vec3 wxv = cross3(gyro, s.vel_b);
     const Vec3 vel_old = s.vel;
     euler_update(s, gyro, dt);
-    s.vel_b.x = s.vel_b.x + (accel.x + cg.x) * dt - wxv.x * dt;
-    s.vel_b.y = s.vel_b.y + (accel.y + cg.y) * dt - wxv.y * dt;
-    s.vel_b.z = s.vel_b.z + (accel.z + cg.z) * dt - wxv.z * dt;
+    if (odo) {
+      s.vel_b = Vec3{accel.x, 0.0, 0.0};
+    } else {
+      s.vel_b.x = s.vel_b.x + (accel.x + cg.x) * dt - wxv.x * dt;
+      s.vel_b.y = s.vel_b.y + (accel.y + cg.y) * dt - wxv.y * dt;
+      s.vel_b.z = s.vel_b.z + (accel.z + cg.z) * dt - wxv.z * dt;
+    }
     refresh_trig<RF, SPLIT>(s, role);
     const Dcm c = dcm_from_sincos(s.sc);
     s.vel = mul_t(c, s.vel_b);
@@ -242,13 +250,18 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     const Vec3 cor = cross3(w2, s.vel);
     const Vec3 vel_old = s.vel;
     euler_update(s, w_nb, dt);
-    s.vel.x = vel_old.x + (fa.x - cor.x) * dt;
-    s.vel.y = vel_old.y + (fa.y - cor.y) * dt;
-    s.vel.z = vel_old.z + (fa.z + g - cor.z) * dt;
     s.pos.x += vel_old.x * inv_rm * dt;
     s.pos.y += vel_old.y * inv_rn * inv_cl * dt;
     s.pos.z += (-vel_old.z) * dt;
     refresh_trig<RF, SPLIT>(s, role);
+    if (odo) {
+      const Dcm cn = dcm_from_sincos(s.sc);   // c_bn of step i
+      s.vel = mul_t(cn, Vec3{accel.x, 0.0, 0.0});
+    } else {
+      s.vel.x = vel_old.x + (fa.x - cor.x) * dt;
+      s.vel.y = vel_old.y + (fa.y - cor.y) * dt;
+      s.vel.z = vel_old.z + (fa.z + g - cor.z) * dt;
+    }
     // vel_b[i] = c_bn(i).dot(vel[i]) (:172) is not an output of the plugin; not computed
   }
 }

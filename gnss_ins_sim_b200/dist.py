@@ -71,6 +71,50 @@ def combine_phase2(partial2, total_runs):
     return torch.sqrt(p / float(total_runs))
 
 
+def merge_stats(blocks):
+    """Chan et al. pairwise merge of per-rank (count, max|e|, mean, std) -> (max, mean, std) of
+    the union, as robust as np.std's two passes.  blocks: iterable of (n, max[nc], mean[nc],
+    std[nc]) numpy; empty shards (n = 0) are skipped."""
+    n_a, mx_a, mean_a, m2_a = 0, None, None, None
+    for n_b, mx_b, mean_b, std_b in blocks:
+        n_b = int(n_b)
+        if n_b == 0:
+            continue
+        m2_b = np.asarray(std_b, dtype=np.float64) ** 2 * n_b
+        if n_a == 0:
+            n_a, mx_a, mean_a, m2_a = n_b, np.array(mx_b, dtype=np.float64), \
+                np.array(mean_b, dtype=np.float64), m2_b
+            continue
+        n = n_a + n_b
+        delta = mean_b - mean_a
+        mean_a = mean_a + delta * (n_b / n)
+        m2_a = m2_a + m2_b + delta * delta * (n_a * n_b / n)
+        mx_a = np.maximum(mx_a, mx_b)
+        n_a = n
+    return np.stack([mx_a, mean_a, np.sqrt(m2_a / n_a)]), n_a
+
+
+def combine_local_stats(stats, local_runs):
+    """stats [3, nc] = (max|e|, mean, std) of this rank's `local_runs` runs (numpy; anything if
+    local_runs == 0) -> [3, nc] of all ranks' runs: ONE all_gather of 3 nc + 1 doubles."""
+    stats = np.asarray(stats, dtype=np.float64)
+    if not initialised():
+        return stats
+    nc = stats.shape[1]
+    dev = _comm_device()
+    mine = torch.zeros(3 * nc + 1, dtype=torch.float64)
+    if local_runs:
+        mine[:3 * nc] = torch.from_numpy(stats.reshape(-1))
+    mine[3 * nc] = float(local_runs)
+    mine = mine.to(dev)
+    outs = [torch.empty_like(mine) for _ in range(world())]
+    td.all_gather(outs, mine)
+    host = torch.stack(outs).cpu().numpy()
+    blocks = [(row[3 * nc], row[0:nc], row[nc:2 * nc], row[2 * nc:3 * nc]) for row in host]
+    merged, _ = merge_stats(blocks)
+    return merged
+
+
 def ensemble_stats(end_err, total_runs):
     """[3, ncomp] numpy = max|e|, mean, std over ALL ranks' runs.
     end_err: this rank's CUDA [R_local, ncomp] (or None if it owns no runs)."""

@@ -72,6 +72,27 @@ def free_integration(ref_frame, fs, gyro, accel, ini, earth_rot=True, layout=LAY
     return att, pos, vel
 
 
+def free_integration_odo(ref_frame, fs, gyro, odo, ini, earth_rot=True, layout=LAYOUT_RUN_MAJOR,
+                         run_offset=0, lanes_per_run=0):
+    """K2, odometer variant.  gyro [R,n,3] / odo [R,n] (RUN_MAJOR) or [n,3,R] / [n,R]."""
+    _require_cuda()
+    lib = _lib.load()
+    if layout == LAYOUT_RUN_MAJOR:
+        R, n, _ = gyro.shape
+        assert tuple(odo.shape) == (R, n)
+    else:
+        n, _, R = gyro.shape
+        assert tuple(odo.shape) == (n, R)
+    att = torch.empty_like(gyro)
+    pos = torch.empty_like(gyro)
+    vel = torch.empty_like(gyro)
+    _lib.check(lib.b2ins_free_integration_odo_f64(
+        int(ref_frame), float(fs), R, n, _ptr(gyro), _ptr(odo), layout, _ptr(ini),
+        ini.shape[0], ini.shape[1], int(run_offset), int(bool(earth_rot)),
+        _ptr(att), _ptr(pos), _ptr(vel), int(lanes_per_run), _stream()))
+    return att, pos, vel
+
+
 def imu_noise(fs, runs, ref_gyro, ref_accel, gyro_err, accel_err, seed, run_offset=0,
               vib_gyro=None, vib_accel=None, layout=LAYOUT_RUN_MAJOR, dump_z=False):
     """K1.  ref_gyro/ref_accel: CUDA f64 [n,3]; *_err: imu_model dicts.
@@ -102,12 +123,15 @@ class McResult:
         self.proc_stats = None   # [R,3,9] max|e|, mean, std per run (stats_start >= 0)
         self.att = self.pos = self.vel = None   # [dump_runs,n,3]
         self.gyro = self.accel = None           # [dump_runs,n,3]
+        self.odo = None                         # [dump_runs,n] (odometer variant)
         self.lanes_per_run = 0
 
 
 def make_mc_config(ref_frame, fs, n, runs, seed, gyro_err, accel_err, ini_sets, ini_rows,
                    earth_rot=True, run_offset=0, vib_gyro=None, vib_accel=None,
-                   lanes_per_run=0, stats_start=-1, dump_runs=0, ini_offset=None):
+                   lanes_per_run=0, stats_start=-1, dump_runs=0, ini_offset=None,
+                   odo_err=None, ref_odo=None):
+    """odo_err {'scale','stdv'} + ref_odo (CUDA f64 [n]) select the odometer variant."""
     cfg = _lib.McConfig()
     cfg.ref_frame = int(ref_frame)
     cfg.earth_rot = int(bool(earth_rot))
@@ -126,6 +150,14 @@ def make_mc_config(ref_frame, fs, n, runs, seed, gyro_err, accel_err, ini_sets, 
     cfg.lanes_per_run = int(lanes_per_run)
     cfg.stats_start = int(stats_start)
     cfg.dump_runs = int(dump_runs)
+    cfg.algo = 0
+    if odo_err is not None:
+        assert ref_odo is not None and ref_odo.is_cuda and ref_odo.dtype == torch.float64
+        cfg.algo = 1
+        cfg.odo_scale = float(odo_err['scale'])
+        cfg.odo_stdv = float(odo_err['stdv'])
+        cfg.ref_odo = ref_odo.data_ptr()
+        cfg._keep = ref_odo            # keep the tensor alive with the config
     return cfg
 
 
@@ -155,8 +187,10 @@ def mc_free_integration(cfg, ref_gyro, ref_accel, ref_nav, ini, want_state=False
         res.att = res.pos = res.vel = None
     if dump_imu and D > 0:
         res.gyro, res.accel = buf(res.gyro, (D, n, 3)), buf(res.accel, (D, n, 3))
+        res.odo = buf(res.odo, (D, n)) if cfg.algo == 1 else None
     else:
-        res.gyro = res.accel = None
+        res.gyro = res.accel = res.odo = None
+    cfg.dump_odo = res.odo.data_ptr() if res.odo is not None else None
     _lib.check(lib.b2ins_mc_free_integration_f64(
         ctypes.byref(cfg), _ptr(ref_gyro), _ptr(ref_accel), _ptr(ref_nav), _ptr(ini),
         _ptr(res.end_err), _ptr(res.end_state), _ptr(res.proc_stats),

@@ -32,6 +32,7 @@ import torch
 
 from . import engine, dist
 from .free_integration import FreeIntegration
+from .free_integration_odo import FreeIntegration as FreeIntegrationOdo
 from .allan_analysis import Allan
 
 D2R = math.pi / 180
@@ -150,6 +151,8 @@ def load_trajectory(src):
     for k in need:
         if out[k].shape != (n, 3):
             raise ValueError('trajectory %s must be (n,3)' % k)
+    if 'ref_odo' in src:
+        out['ref_odo'] = np.ascontiguousarray(src['ref_odo'], dtype=np.float64).reshape(-1)
     if 'time' in src:
         out['time'] = np.asarray(src['time'], dtype=np.float64)
     if 'ini' in src:
@@ -157,7 +160,7 @@ def load_trajectory(src):
     return out
 
 
-def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetometer=False):
+def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetometer=False, odo=False):
     """Motion-definition csv/string -> trajectory via the reference's CPU path generator
     (pathgen.path_gen, pathgen.py:26-329), driven exactly as Sim.__gen_data_from_pathgen
     does (ins_sim.py:444-472, :578-640)."""
@@ -192,13 +195,14 @@ def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetomete
     else:
         mobility = np.array(mode, dtype=np.float64)
         mobility[1:3] = mobility[1:3] * D2R
-    output_def = np.array([[1.0, fs], [-1.0, fs], [-1.0, fs]])
+    output_def = np.array([[1.0, fs], [-1.0, fs], [1.0 if odo else -1.0, fs]])
     rtn = pathgen.path_gen(ini_pva, cmd, output_def, mobility, ref_frame, magnetometer)
-    return {'time': rtn['nav'][:, 0] / fs, 'ref_pos': np.ascontiguousarray(rtn['nav'][:, 1:4]),
+    extra = {'ref_odo': np.ascontiguousarray(rtn['odo'][:, 2])} if odo else {}
+    return dict(extra, **{'time': rtn['nav'][:, 0] / fs, 'ref_pos': np.ascontiguousarray(rtn['nav'][:, 1:4]),
             'ref_vel': np.ascontiguousarray(rtn['nav'][:, 4:7]),
             'ref_att': np.ascontiguousarray(rtn['nav'][:, 7:10]),
             'ref_accel': np.ascontiguousarray(rtn['imu'][:, 1:4]),
-            'ref_gyro': np.ascontiguousarray(rtn['imu'][:, 4:7]), 'ini': ini_pva}
+            'ref_gyro': np.ascontiguousarray(rtn['imu'][:, 4:7]), 'ini': ini_pva})
 
 
 class LazyRuns(Mapping):
@@ -317,7 +321,8 @@ class Sim(object):
                     'logged-data directories are read by the reference Sim; feed the arrays to '
                     'FreeIntegration.run_batch / Allan.run_batch instead')
             traj = trajectory_from_motion_def(self.fs[0], src, self.ref_frame, self.mode,
-                                              bool(self.imu and self.imu.magnetometer))
+                                              bool(self.imu and self.imu.magnetometer),
+                                              bool(self.imu and self.imu.odo))
         else:
             raise TypeError('motion_def must be a trajectory dict, an .npz path or a motion '
                             'definition csv/string')
@@ -330,6 +335,8 @@ class Sim(object):
         d['ref_pos'], d['ref_vel'], d['ref_att_euler'] = traj['ref_pos'], traj['ref_vel'], traj['ref_att']
         d['ref_accel'], d['ref_gyro'] = traj['ref_accel'], traj['ref_gyro']
         d['ref_att_quat'] = euler2quat_zyx(traj['ref_att'])
+        if 'ref_odo' in traj:
+            d['ref_odo'] = traj['ref_odo']
         self._nav_end = np.concatenate([traj['ref_att'][-1], traj['ref_pos'][-1], traj['ref_vel'][-1]])
         self._nav_cache = None
         self._dev_cache = None
@@ -376,9 +383,13 @@ class Sim(object):
         self._shard = dist.shard(R)
         self.data['accel'] = LazyRuns(self, 'accel', R)
         self.data['gyro'] = LazyRuns(self, 'gyro', R)
+        if getattr(self.imu, 'odo', False):
+            if 'ref_odo' not in self._traj:
+                raise ValueError('imu.odo is on but the trajectory has no ref_odo')
+            self.data['odo'] = LazyRuns(self, 'odo', R)
         if self.algo is not None:
             for i, a in enumerate(self.algo):
-                if isinstance(a, FreeIntegration):
+                if isinstance(a, FreeIntegration):     # incl. the odometer variant
                     self._run_free_integration(i, a)
                 elif isinstance(a, Allan):
                     self._run_allan(i, a)
@@ -400,7 +411,17 @@ class Sim(object):
             run_offset=self.run_base + r0, ini_offset=self._mc[ai]['base'] + r0,
             vib_gyro=vib_gyro, vib_accel=vib_acc,
             lanes_per_run=self.lanes_per_run or algo.lanes_per_run, stats_start=stats_start,
-            dump_runs=dump_runs)
+            dump_runs=dump_runs, **self._odo_args(algo))
+
+    def _odo_args(self, algo):
+        """Odometer variant: noise model (imu.odo_err) and the true forward speed on the device."""
+        if not isinstance(algo, FreeIntegrationOdo):
+            return {}
+        if not getattr(self.imu, 'odo', False) or 'ref_odo' not in self._traj:
+            raise ValueError('free_integration_odo needs IMU(odo=True) and a trajectory with ref_odo')
+        if getattr(self, '_ref_odo_dev', None) is None:
+            self._ref_odo_dev = engine.to_device(self._traj['ref_odo'])
+        return {'odo_err': self.imu.odo_err, 'ref_odo': self._ref_odo_dev}
 
     def _vib_pair(self, runs, r0):
         """(vib_gyro, vib_accel) arguments for experiment runs [r0, r0+runs): parsed dicts, or
@@ -428,24 +449,28 @@ class Sim(object):
         name = self.algo_name(i)
         lo, hi = self._shard
         self._mc[i] = {'base': algo.run_times, 'end_err': None}   # plugin's run counter at run 0
-        if dist.world() == 1:
-            # single GPU: the plan path (pinned staging, one H2D, K12, K3, one D2H)
-            cfg = self._mc_config(i, hi - lo, lo)
-            t = self._traj
-            plan = engine.get_plan(cfg.n, cfg.runs, cfg.ini_sets, cfg.ini_rows)
-            err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav_end, algo.ini_sets)
+        if not isinstance(algo, FreeIntegrationOdo):
+            # the plan path on this rank's shard (pinned staging, one H2D, K12, K3, one D2H);
+            # with several ranks the [3][9] shard statistics are merged by one all_gather
+            err, stats = np.zeros((0, 9)), np.zeros((3, 9))
+            if hi > lo:
+                cfg = self._mc_config(i, hi - lo, lo)
+                t = self._traj
+                plan = engine.get_plan(cfg.n, cfg.runs, cfg.ini_sets, cfg.ini_rows)
+                err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav_end, algo.ini_sets)
             self._mc[i]['end_err'] = err
-            self.err_stats[name] = stats
+            self.err_stats[name] = dist.combine_local_stats(stats, hi - lo)
         else:
             d = self._dev
-            res = None
+            err, stats = np.zeros((0, 9)), np.zeros((3, 9))
             if hi > lo:
                 cfg = self._mc_config(i, hi - lo, lo)
                 res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
                                                  algo.ini_device())
-            self.err_stats[name] = dist.ensemble_stats(res.end_err if res is not None else None,
-                                                       self.sim_count)
-            self._mc[i]['end_err'] = res.end_err.cpu().numpy() if res is not None else np.zeros((0, 9))
+                stats = engine.error_stats(res.end_err).cpu().numpy()
+                err = res.end_err.cpu().numpy()
+            self._mc[i]['end_err'] = err
+            self.err_stats[name] = dist.combine_local_stats(stats, hi - lo)
         algo.run_times += self.sim_count
         for out in ('att_euler', 'pos', 'vel'):
             prev = self.data.get(out)
@@ -533,15 +558,24 @@ class Sim(object):
                                                  algo.ini_device(), dump_nav=True, dump_imu=True)
                 self._cache[key] = {'att_euler': res.att.cpu().numpy(), 'pos': res.pos.cpu().numpy(),
                                     'vel': res.vel.cpu().numpy()}
-                self._cache[('imu', blk)] = {'gyro': res.gyro.cpu().numpy(),
-                                             'accel': res.accel.cpu().numpy()}
+                imu_hist = {'gyro': res.gyro.cpu().numpy(), 'accel': res.accel.cpu().numpy()}
+                if res.odo is not None:
+                    imu_hist['odo'] = res.odo.cpu().numpy()
+                self._cache.setdefault(('imu', blk), {}).update(imu_hist)
             return self._cache[key][out][run - blk * self.history_block]
         key = ('imu', blk)
-        if key not in self._cache:
+        if key not in self._cache or name not in self._cache[key]:
             r0 = blk * self.history_block
             r1 = min(self.sim_count, r0 + self.history_block)
-            gyro, accel = self._noise_block(r0, r1)
-            self._cache[key] = {'gyro': gyro.cpu().numpy(), 'accel': accel.cpu().numpy()}
+            hist = self._cache.setdefault(key, {})
+            if name == 'odo':      # pathgen.odo_gen stream: a zero-length odometer experiment
+                ai = [i for i, a in enumerate(self.algo or []) if isinstance(a, FreeIntegrationOdo)]
+                if not ai:
+                    raise KeyError('odo histories are produced with the free_integration_odo plugin')
+                self._history((ai[0], 'pos'), run)
+            else:
+                gyro, accel = self._noise_block(r0, r1)
+                hist.update({'gyro': gyro.cpu().numpy(), 'accel': accel.cpu().numpy()})
         return self._cache[key][name][run - blk * self.history_block]
 
     # ---- results --------------------------------------------------------------

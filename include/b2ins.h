@@ -92,6 +92,15 @@ typedef struct b2ins_mc_config {
   int32_t stats_start;    /* first sample index of the per-run process-error statistics
                              (ins_data_manager.py:761-795); < 0 = end-point errors only */
   int64_t dump_runs;      /* full histories are written for local runs [0, dump_runs) */
+  /* algorithm: 0 = FreeIntegration (free_integration.py), 1 = the odometer variant
+   * (demo_algorithms/free_integration_odo.py:63-160: body velocity = [odometer, 0, 0]) with
+   * pathgen.odo_gen noise (pathgen.py:627-641): odo = odo_scale*ref_odo + odo_stdv*randn */
+  int32_t algo;
+  int32_t reserved;
+  double odo_scale;
+  double odo_stdv;
+  const double* ref_odo;  /* algo 1: DEVICE pointer [n], true forward speed (pathgen 'odo') */
+  double* dump_odo;       /* algo 1, nullable: DEVICE pointer [dump_runs][n] odometer histories */
 } b2ins_mc_config;
 
 /* ---- housekeeping ------------------------------------------------------ */
@@ -118,6 +127,15 @@ int b2ins_free_integration_f64_host(int ref_frame, double fs, int64_t runs, int6
                                     const double* ini, int ini_sets, int ini_rows,
                                     int64_t run_offset, int earth_rot,
                                     double* att, double* pos, double* vel, int lanes_per_run);
+
+/* The odometer variant with supplied data: FreeIntegration.run of
+ * demo_algorithms/free_integration_odo.py:63-160.  odo: [R][n] (RUN_MAJOR) or [n][R]. */
+int b2ins_free_integration_odo_f64(int ref_frame, double fs, int64_t runs, int64_t n,
+                                   const double* gyro, const double* odo, int layout,
+                                   const double* ini, int ini_sets, int ini_rows,
+                                   int64_t run_offset, int earth_rot,
+                                   double* att, double* pos, double* vel,
+                                   int lanes_per_run, void* stream);
 
 /* ---- K1: IMU sensor-error generator --------------------------------------
  * Replaces pathgen.acc_gen / gyro_gen / bias_drift (pathgen.py:441-594) for `runs` runs:

@@ -41,7 +41,9 @@ def test_abi_structs_match_header_layout():
     from gnss_ins_sim_b200 import _lib
     assert ctypes.sizeof(_lib.SensorErr) == 96
     assert ctypes.sizeof(_lib.Vib) == 48
-    assert ctypes.sizeof(_lib.McConfig) == 8 + 8 + 8 * 4 + 8 + 2 * 96 + 2 * 48 + 16 + 8
+    assert ctypes.sizeof(_lib.McConfig) == 408
+    assert _lib.McConfig.dump_runs.offset == 360 and _lib.McConfig.algo.offset == 368
+    assert _lib.McConfig.ref_odo.offset == 392
 
 
 def test_allan_num_tau_matches_reference_rule():
@@ -260,6 +262,23 @@ def test_shard_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_merge_stats_is_as_good_as_two_pass():
+    from gnss_ins_sim_b200 import dist
+    rng = np.random.RandomState(1)
+    x = rng.randn(1000, 9) * 1e-3 + 1e3          # mean >> std: one-pass sum-of-squares would fail
+    cuts = [0, 1, 1, 400, 401, 1000]              # includes an empty shard and a 1-run shard
+    blocks = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = x[a:b]
+        blocks.append((b - a, np.abs(part).max(0) if b > a else np.zeros(9),
+                       part.mean(0) if b > a else np.zeros(9), part.std(0) if b > a else np.zeros(9)))
+    merged, n = dist.merge_stats(blocks)
+    assert n == 1000
+    assert_close(merged[1], x.mean(0), 1e-14, 0.0, 'mean')
+    assert_close(merged[2], x.std(0), 1e-10, 0.0, 'std')
+    assert np.array_equal(merged[0], np.abs(x).max(0))
+
+
 def _gloo_worker(rank, world, port, tmp):
     import torch
     import torch.distributed as td
@@ -275,13 +294,15 @@ def _gloo_worker(rank, world, port, tmp):
     partial = torch.cat([mine.sum(0), mine.abs().max(0).values])
     mean, mx, tot = dist.combine_phase1(partial, hi - lo, 9)
     std = dist.combine_phase2(((mine - mean) ** 2).sum(0), tot)
+    loc = mine.numpy()
+    merged = dist.combine_local_stats(np.stack([np.abs(loc).max(0), loc.mean(0), loc.std(0)]), hi - lo)
     rows = dist.gather_rows(mine, total)
     traj = None
     if rank == 0:
         traj = {k: rng.randn(50, 3) for k in ('ref_pos', 'ref_vel', 'ref_att', 'ref_accel', 'ref_gyro')}
     got = dist.broadcast_trajectory(traj)
     np.savez(os.path.join(tmp, 'r%d.npz' % rank), mean=mean.numpy(), mx=mx.numpy(), std=std.numpy(),
-             tot=tot, rows=rows, gyro=got['ref_gyro'], lo=lo, hi=hi)
+             tot=tot, rows=rows, gyro=got['ref_gyro'], lo=lo, hi=hi, merged=merged)
     td.destroy_process_group()
 
 
@@ -299,5 +320,7 @@ def test_two_rank_statistics_over_gloo(tmp_path):
         assert_close(z['mx'], np.abs(err).max(0), 0.0, 0.0, 'max')
         assert_close(z['std'], err.std(0), 1e-12, 0.0, 'std')
         assert np.array_equal(z['rows'], err)
+        assert_close(z['merged'], np.stack([np.abs(err).max(0), err.mean(0), err.std(0)]), 1e-12, 1e-12,
+                     'one-collective merge')
         gyro0 = z['gyro'] if gyro0 is None else gyro0
         assert np.array_equal(z['gyro'], gyro0) and z['gyro'].shape == (50, 3)

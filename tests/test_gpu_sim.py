@@ -154,3 +154,37 @@ def test_sim_allan_and_foreign_plugins(gpu):
     wb = sim.get_data(['wb'])[0]
     assert sorted(wb.keys()) == ['mean_0', 'mean_1']
     assert_close(wb['mean_1'], g['gyro'][1].mean(0) * 100.0, 1e-12, 1e-6, 'foreign plugin')
+
+
+@pytest.mark.parametrize('rf', [1, 0])
+def test_odometer_variant_matches_reference(gpu, rf):
+    """free_integration_odo (demo_free_integration.py's algo1): K2 with supplied odometer data,
+    and the fused path with pathgen.odo_gen noise through Sim, against the reference."""
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration_odo import FreeIntegration as FreeIntegrationOdo
+    g = load_golden('philox_90deg_mid_rf%d_odo.npz' % rf)
+    R = g['odo'].shape[0]
+    for lanes in (1, 8, 32):
+        algo = FreeIntegrationOdo(g['ini'], lanes_per_run=lanes)
+        assert algo.input == ['ref_frame', 'fs', 'gyro', 'odo']
+        att, pos, vel = algo.run_batch(rf, 100.0, g['gyro'], g['odo'])
+        assert np.abs(wrap_pi(att - g['att'])).max() < 1e-9
+        assert_close(pos, g['pos'], 1e-9, 1.0 if rf == 1 else 1e-7, 'pos')
+        assert_close(vel, g['vel'], 1e-9, 1.0, 'vel')
+    algo = FreeIntegrationOdo(g['ini'])
+    algo.run([rf, 100.0, g['gyro'][2], g['odo'][2]])          # plugin protocol, one run
+    assert_close(algo.get_results()[2], g['vel'][2], 1e-9, 1.0, 'vel single')
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=False, odo=True,
+                        odo_opt={'scale': float(g['odo_scale']), 'stdv': float(g['odo_stdv'])})
+    traj = dict(_traj(g), ref_odo=g['ref_odo'])
+    sim = Sim([100.0, 0.0, 0.0], traj, ref_frame=rf, imu=imu, algorithm=FreeIntegrationOdo(g['ini']),
+              seed=int(g['seed']))
+    sim.run(R)
+    for dn in ('att_euler', 'pos', 'vel'):
+        st = sim.get_error_stats(dn, -1, angle=(dn == 'att_euler'))
+        for k in ('max', 'avg', 'std'):
+            assert_close(st[k], g['stat_%s_%s' % (dn, k)], 1e-6, 1e-3, '%s %s' % (dn, k))
+    assert_close(sim.get_data(['odo'])[0][3], g['odo'][3], 1e-12, 1.0, 'odo history')
+    assert_close(sim.get_data(['pos'])[0]['algo0_4'], g['pos'][4], 1e-9, 1.0 if rf == 1 else 1e-7, 'pos hist')
+    assert_close(sim.get_data(['accel'])[0][1], g['accel'][1], 1e-12, 1.0, 'accel history')

@@ -121,3 +121,17 @@ def test_golden_survey_values():
                                    9.5098666116010674e-05], 1e-13)
     assert_close(g['pos'][0, -1], [-2707376.9803619734, 4688713.859123157, 3360102.3087808033],
                  1e-15)
+
+
+@pytest.mark.parametrize('rf', [0, 1])
+def test_odometer_variant_oracle(rf):
+    """odo_gen + free_integration_odo restatements == reference fed the same normals."""
+    g = load_golden('philox_90deg_mid_rf%d_odo.npz' % rf)
+    R, n = g['odo'].shape
+    zo = onp.odo_normals(n, g['run_ids'], int(g['seed']))
+    odo = onp.odo_gen(g['ref_odo'], {'scale': float(g['odo_scale']), 'stdv': float(g['odo_stdv'])}, zo)
+    assert_close(odo, g['odo'], TIGHT, what='odo')
+    att, pos, vel = onp.free_integration_odo(rf, 100.0, g['gyro'], odo, np.tile(g['ini'], (R, 1)))
+    assert_close(att, g['att'], 1e-10, what='att')
+    assert_close(pos, g['pos'], 1e-10, what='pos')
+    assert_close(vel, g['vel'], 1e-10, what='vel')
