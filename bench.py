@@ -222,13 +222,15 @@ def run_b200(args):
     res = engine.McResult()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
+    merger = dist.StatsMerger(9) if world > 1 else None
+
     def step():
         engine.mc_free_integration(cfg, ref_gyro, ref_accel, nav, ini, out=res)
         st = engine.error_stats(res.end_err)
         if world == 1:
             return st
         # N > 1: the shard statistics are merged (Chan) after ONE all_gather of 28 doubles
-        return dist.combine_local_stats(st.cpu().numpy(), R)
+        return merger(st, R)
 
     def barrier():
         if world > 1:

@@ -35,12 +35,13 @@ class Allan(object):
         a = engine.to_device(accel)
         g = engine.to_device(gyro)
         R, n, _ = a.shape
-        x = torch.stack([a, g])                   # [2, R, n, 3]
-        avar, tau = engine.allan(fs, x, n, 2 * R * 3, inner=3, outer_stride=3 * n, sample_stride=3)
-        ad = torch.sqrt(avar).reshape(2, R, 3, -1).permute(0, 1, 3, 2).contiguous()
+        out = []
+        for x in (a, g):          # each [R, n, 3]: 3R interleaved series, read in place (no copy)
+            avar, tau = engine.allan(fs, x, n, R * 3, inner=3, outer_stride=3 * n, sample_stride=3)
+            out.append(torch.sqrt(avar).reshape(R, 3, -1).permute(0, 2, 1).contiguous())
         if to_host:
-            return tau.cpu().numpy(), ad[0].cpu().numpy(), ad[1].cpu().numpy()
-        return tau, ad[0], ad[1]
+            return tau.cpu().numpy(), out[0].cpu().numpy(), out[1].cpu().numpy()
+        return tau, out[0], out[1]
 
     def get_results(self):
         return self.results

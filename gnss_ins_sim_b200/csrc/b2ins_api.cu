@@ -114,7 +114,7 @@ int auto_lanes(int64_t runs) {
   // warps = runs*G/32 <= 4*SMs -- and never more lanes than that needs.
   const int64_t smsp = static_cast<int64_t>(sm_count()) * 4;
   int g = 32;
-  while (g > 1 && runs * g > smsp * 32) g >>= 1;
+  while (g > 1 && runs * g * 2 > smsp * 32 * 3) g >>= 1;   // warps <= 1.5 per sub-partition
   return g;
 }
 

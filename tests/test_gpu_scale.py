@@ -132,3 +132,36 @@ def test_large_ensemble_properties(eng):
     expect = 0.05 / 60 * np.sqrt(n / fs)            # vrw * sqrt(T)
     assert (np.abs(a[2, 6:9] / expect - 1) < 0.2).all()
     assert (np.abs(a[1, 6:9]) < 5 * a[2, 6:9] / np.sqrt(65536)).all()
+
+
+def test_config4_length_allan_through_sim(eng):
+    """BASELINE config 4 shape: static 10 h @400 Hz (n = 14.4 M), 'low-accuracy' IMU, the Allan
+    plugin through Sim (K1 noise + K4), 4 runs here instead of 256; one run/channel is checked
+    against the C oracle's noise + allan_var, all channels against the white-noise law."""
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.allan_analysis import Allan
+    n, fs, R, seed = 14400000, 400.0, 4, 5
+    ref_gyro = np.zeros((n, 3))
+    ref_accel = np.tile(np.array([4.9, 0.0, -8.487]), (n, 1))        # 30 deg pitch, static
+    traj = {'ref_pos': np.zeros((n, 3)), 'ref_vel': np.zeros((n, 3)), 'ref_att': np.zeros((n, 3)),
+            'ref_accel': ref_accel, 'ref_gyro': ref_gyro}
+    imu = imu_model.IMU(accuracy='low-accuracy', axis=6, gps=False)
+    sim = Sim([fs, 0.0, 0.0], traj, ref_frame=1, imu=imu, algorithm=Allan(), seed=seed)
+    sim.run(R)
+    tau, ada, adg = sim.get_data(['algo_time', 'ad_accel', 'ad_gyro'])
+    t = tau['algo0_0']
+    assert t.shape == (55,) and abs(t[-1] - 2500.0) < 1e-9 and ada['algo0_3'].shape == (55, 3)
+    # run 2, gyro z and accel x against the oracle (noise from oracle.c, Allan from oracle.c)
+    og, oa = oracle_c.imu_noise(fs, ref_gyro, ref_accel, LOW_G, LOW_A, seed, [2])
+    av, ot = oracle_c.allan_var(np.ascontiguousarray(og[0, :, 2]), fs)
+    assert_close(adg['algo0_2'][:, 2], np.sqrt(av), 1e-8, 0.0, 'ad_gyro z')
+    av, _ = oracle_c.allan_var(np.ascontiguousarray(oa[0, :, 0]), fs)
+    assert_close(ada['algo0_2'][:, 0], np.sqrt(av), 1e-8, 0.0, 'ad_accel x')
+    assert_close(t, ot, 1e-12, 0.0, 'tau')
+    # white-noise regime (tau << bias correlation time): AD(tau) = arw / sqrt(tau)
+    arw = LOW_G['arw'][0]
+    k = np.where((t >= 0.01) & (t <= 1.0))[0]
+    for r in range(R):
+        ratio = adg['algo0_%d' % r][k, :] / (arw / np.sqrt(t[k]))[:, None]
+        assert (np.abs(ratio - 1) < 0.05).all()
