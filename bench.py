@@ -48,9 +48,13 @@ SEED = 12345
 TRAJ = os.path.join(ROOT, 'tests', 'golden', 'traj_90deg_turn_100hz_rf1.npz')
 WORKLOAD = ("free_integration, motion_def-90deg_turn.csv (n=1000 @100Hz), 'mid-accuracy' IMU, "
             "ref_frame=1, 1000 MC runs per GPU")
-# FP64-pipe instructions per run-step of mc_kernel (ncu smsp__inst_executed_pipe_fp64 /
-# run-steps, profiles/): filled from the round's ncu capture; None = not yet measured
-FP64_INST_PER_RUN_STEP = None
+# FP64 thread-instructions (DFMA/DMUL/DADD/DSETP) one run-step costs in mc_kernel, by lane-group
+# width, from the ncu source-level counts in profiles/ncu_mc_kernel_r01_v3_*.json (lanes of a
+# group replicate the serial step, so wide groups spend more instructions per run-step)
+FP64_INST_PER_RUN_STEP = {16: 2145.6, 1: 648.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of one mc_kernel launch at this workload
+# (profiles/ncu_mc_kernel_r01_v3_cfg2_lanes16.json): the trajectory; the 72 KB of results stay in L2
+NCU_DRAM_BYTES_PER_LAUNCH = 129280
 
 
 def load_workload():
@@ -222,15 +226,24 @@ def run_b200(args):
     res = engine.McResult()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
-    merger = dist.StatsMerger(9) if world > 1 else None
+    merger = p2p = None
+    exchange = 'none'
+    if world > 1:
+        try:        # K3x: statistics + exchange + merge fused in one kernel over NVLink peer memory
+            p2p = dist.P2PStats(9)
+            exchange = 'fused peer-memory kernel (K3x)'
+        except Exception as e:     # no symmetric memory on this box: NCCL all_gather of 28 doubles
+            sys.stderr.write('P2PStats unavailable (%s); using NCCL all_gather\n' % e)
+            merger = dist.StatsMerger(9)
+            exchange = 'NCCL all_gather + host merge'
 
     def step():
         engine.mc_free_integration(cfg, ref_gyro, ref_accel, nav, ini, out=res)
-        st = engine.error_stats(res.end_err)
         if world == 1:
-            return st
-        # N > 1: the shard statistics are merged (Chan) after ONE all_gather of 28 doubles
-        return merger(st, R)
+            return engine.error_stats(res.end_err)
+        if p2p is not None:
+            return p2p(res.end_err, R).cpu().numpy()
+        return merger(engine.error_stats(res.end_err), R)
 
     def barrier():
         if world > 1:
@@ -289,9 +302,14 @@ def run_b200(args):
     fp64 = {'bound': 'fp64-issue', 'peak_dfma_per_s': dfma.value, 'peak_source': 'measured live '
             '(b2ins_diag_dfma_rate)', 'kernel_run_steps_per_s': k_rate,
             'dfma_slots_per_run_step': dfma.value / k_rate}
-    if FP64_INST_PER_RUN_STEP:
-        fp64['fp64_inst_per_run_step'] = FP64_INST_PER_RUN_STEP
-        fp64['frac'] = FP64_INST_PER_RUN_STEP * k_rate / dfma.value
+    lanes_used = args.lanes or 16      # auto_lanes(1000) = 16 on a 148-SM part
+    if lanes_used in FP64_INST_PER_RUN_STEP:
+        fp64['lanes_per_run'] = lanes_used
+        fp64['fp64_inst_per_run_step'] = FP64_INST_PER_RUN_STEP[lanes_used]
+        fp64['frac'] = FP64_INST_PER_RUN_STEP[lanes_used] * k_rate / dfma.value
+        fp64['frac_note'] = ('FP64 instructions issued / measured FP64-FMA issue rate; 1000 runs leave '
+                             'the serial recurrence latency-bound (one warp per SM sub-partition); the '
+                             'same kernel reaches 0.56 at 10^6 runs (profiles/)')
 
     if args.quick:
         if rank == 0:
@@ -336,14 +354,14 @@ def run_b200(args):
         'config': {'workload': WORKLOAD, 'runs': total_runs, 'runs_per_gpu': R, 'samples': n,
                    'global_run_steps': total_runs * n, 'l2_flush_between_steps': True,
                    'lanes_per_run': args.lanes or 'auto', 'seed': SEED,
-                   'parallelism': 'runs sharded x%d, one all_gather of the [3][9] shard statistics' % world},
+                   'parallelism': 'runs sharded x%d; statistics exchange: %s' % (world, exchange)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'api': 'gnss_ins_sim_b200.sim.Sim.run + get_error_stats'},
         # per step: mc_kernel + stats_small_kernel (the NCCL all_gather is not ours)
         'gpu_launches': args.steps * 2,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': achieved / hbm_peak, 'traffic': None,
+                     'frac': achieved / hbm_peak, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                      'kernel': 'mc_kernel (K12)', 'kernel_ms': k_ms,
                      'algorithmic_bytes_per_launch': alg_bytes,

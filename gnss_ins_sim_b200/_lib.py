@@ -68,6 +68,7 @@ SIGNATURES = {
     'b2ins_error_partial_f64': (_I, [_L, _I, _P, _P, _P, _P]),
     'b2ins_error_partial2_f64': (_I, [_L, _I, _P, _P, _P, _P, _P]),
     'b2ins_error_stats_f64': (_I, [_L, _I, _P, _P, _P, _P]),
+    'b2ins_error_stats_exchange_f64': (_I, [_L, _I, _P, _I, _I, ctypes.POINTER(ctypes.c_uint64), _U64, _P, _P, _P]),
     'b2ins_allan_workspace_bytes': (_L, [_L, _L]),
     'b2ins_allan_f64': (_I, [_D, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P]),
     'b2ins_allan_f64_host': (_I, [_D, _L, _L, _P, _L, _L, _L, _P, _P]),

@@ -676,6 +676,30 @@ int b2ins_error_stats_f64(int64_t runs, int ncomp, const double* err, double* st
   return B2INS_OK;
 }
 
+int b2ins_error_stats_exchange_f64(int64_t runs, int ncomp, const double* err, int rank, int world,
+                                   const uint64_t* windows, uint64_t seq, double* stats,
+                                   int* timeout_flag, void* stream) {
+  ARG_CHECK(runs >= 0 && ncomp >= 1 && 3 * ncomp + 2 <= kXchgSlot, "bad runs/ncomp");
+  ARG_CHECK(runs * ncomp <= kStatSmallMax, "the fused exchange handles runs*ncomp <= 2^17 per rank");
+  ARG_CHECK(world >= 1 && world <= kXchgMaxWorld && rank >= 0 && rank < world, "bad rank/world");
+  ARG_CHECK(windows && stats && timeout_flag && seq >= 1, "null buffer / seq must start at 1");
+  ARG_CHECK(runs == 0 || err, "null err");
+  XchgParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.runs = runs;
+  p.ncomp = ncomp;
+  p.rank = rank;
+  p.world = world;
+  p.seq = seq;
+  p.err = err;
+  for (int q = 0; q < world; ++q) p.peer[q] = reinterpret_cast<double*>(windows[q]);
+  p.out = stats;
+  p.timeout_flag = timeout_flag;
+  stats_exchange_kernel<<<1, kStatSmallThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
 // ---------------------------------------------------------------- K4 --------
 int64_t b2ins_allan_workspace_bytes(int64_t n, int64_t nseries) {
   return allan_workspace_bytes(n, nseries);

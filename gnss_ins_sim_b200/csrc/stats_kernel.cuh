@@ -128,4 +128,121 @@ stats_small_kernel(int64_t runs, int ncomp, const double* __restrict__ err, doub
   }
 }
 
+// ---- K3x: statistics fused with their exchange over NVLink peer memory ---------------------
+// Multi-GPU ensembles: instead of K3 followed by an NCCL collective, ONE kernel per rank computes
+// the shard statistics, stores (max, mean, std, count) straight into every peer's receive
+// window through peer-mapped (symmetric) memory, raises a flag with a system-scope release
+// store, waits for the other ranks' flags and merges all shards with Chan's update.  The payload
+// is 29 doubles per rank; what is saved is the collective's launch + host round trips.
+constexpr int kXchgSlot = 32;       // doubles per (parity, source rank): 3*9 stats, count, flag
+constexpr int kXchgMaxWorld = 16;
+
+struct XchgParams {
+  int64_t runs;
+  int ncomp, rank, world;
+  uint64_t seq;                      // call counter >= 1; windows are double-buffered on seq & 1
+  const double* err;
+  double* peer[kXchgMaxWorld];       // peer[p]: rank p's window [2][world][kXchgSlot], mapped here
+  double* out;                       // [3][ncomp] merged statistics
+  int* timeout_flag;                 // set to 1 if a peer never showed up
+};
+
+__global__ void __launch_bounds__(kStatSmallThreads)
+stats_exchange_kernel(const __grid_constant__ XchgParams p) {
+  __shared__ double sh[2 * kStatSmallThreads];
+  __shared__ double loc[3 * kStatMaxComp + 1];
+  const int nc = p.ncomp;
+  const int threads = (kStatSmallThreads / nc) * nc;
+  const int c = threadIdx.x % nc;
+  const int64_t total = p.runs * nc;
+  const bool on = threadIdx.x < threads;
+  // ---- local (max, mean, std): same two passes as stats_small_kernel -------------------------
+  double acc = 0.0, mx = 0.0;
+  if (on)
+    for (int64_t i = threadIdx.x; i < total; i += threads) {
+      const double e = p.err[i];
+      acc += e;
+      mx = fmax(mx, fabs(e));
+    }
+  sh[threadIdx.x] = acc;
+  sh[kStatSmallThreads + threadIdx.x] = mx;
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    double s = 0.0, m = 0.0;
+    for (int k = threadIdx.x; k < threads; k += nc) {
+      s += sh[k];
+      m = fmax(m, sh[kStatSmallThreads + k]);
+    }
+    loc[c] = m;
+    loc[nc + c] = p.runs > 0 ? s / static_cast<double>(p.runs) : 0.0;
+  }
+  __syncthreads();
+  const double mu = loc[nc + c];
+  acc = 0.0;
+  if (on)
+    for (int64_t i = threadIdx.x; i < total; i += threads) {
+      const double d = p.err[i] - mu;
+      acc += d * d;
+    }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    double s = 0.0;
+    for (int k = threadIdx.x; k < threads; k += nc) s += sh[k];
+    loc[2 * nc + c] = p.runs > 0 ? sqrt(s / static_cast<double>(p.runs)) : 0.0;
+  }
+  if (threadIdx.x == 0) loc[3 * nc] = static_cast<double>(p.runs);
+  __syncthreads();
+  // ---- push to every rank's window (peer stores over NVLink), then the flags ------------------
+  const int par = static_cast<int>(p.seq & 1);
+  const int64_t slot = (static_cast<int64_t>(par) * p.world + p.rank) * kXchgSlot;
+  if (threadIdx.x <= 3 * nc) {
+    const double v = loc[threadIdx.x];
+    for (int q = 0; q < p.world; ++q) p.peer[q][slot + threadIdx.x] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < p.world) {
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(p.peer[threadIdx.x] + slot + kXchgSlot - 1);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(p.seq) : "memory");
+    // ---- wait for rank threadIdx.x's contribution in MY window -------------------------------
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
+        p.peer[p.rank] + (static_cast<int64_t>(par) * p.world + threadIdx.x) * kXchgSlot + kXchgSlot - 1);
+    unsigned long long seen = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer never launched
+        *p.timeout_flag = 1;
+        break;
+      }
+    } while (seen < p.seq);
+  }
+  __syncthreads();
+  // ---- Chan merge of all shards, one thread per component, fixed rank order -------------------
+  if (threadIdx.x < nc) {
+    const double* win = p.peer[p.rank] + static_cast<int64_t>(par) * p.world * kXchgSlot;
+    double n_a = 0.0, mx_a = 0.0, mean_a = 0.0, m2_a = 0.0;
+    for (int q = 0; q < p.world; ++q) {
+      const double* sl = win + static_cast<int64_t>(q) * kXchgSlot;
+      const double n_b = sl[3 * nc];
+      if (n_b <= 0.0) continue;
+      const double mean_b = sl[nc + c], std_b = sl[2 * nc + c];
+      const double m2_b = std_b * std_b * n_b;
+      if (n_a == 0.0) {
+        n_a = n_b; mx_a = sl[c]; mean_a = mean_b; m2_a = m2_b;
+      } else {
+        const double n = n_a + n_b, delta = mean_b - mean_a;
+        mean_a += delta * (n_b / n);
+        m2_a += m2_b + delta * delta * (n_a * n_b / n);
+        mx_a = fmax(mx_a, sl[c]);
+        n_a = n;
+      }
+    }
+    p.out[c] = mx_a;
+    p.out[nc + c] = mean_a;
+    p.out[2 * nc + c] = n_a > 0.0 ? sqrt(m2_a / n_a) : 0.0;
+  }
+}
+
 }  // namespace b2ins

@@ -137,6 +137,54 @@ class StatsMerger:
         return merge_stats(blocks)[0]
 
 
+class P2PStats:
+    """K3x: shard statistics + exchange + merge in ONE kernel per rank over NVLink peer memory
+    (b2ins_error_stats_exchange_f64).  torch's symmetric memory supplies the peer-mapped
+    windows (plumbing); the kernel, the flags and the merge are ours.  Raises if symmetric
+    memory cannot be set up (callers fall back to StatsMerger / NCCL)."""
+
+    def __init__(self, ncomp=9):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        assert initialised() and td.get_backend() == 'nccl'
+        self._lib, self._check = _lib.load(), _lib.check
+        self.nc, self.w, self.r = ncomp, world(), rank()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        group = td.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.win = symm.empty((2 * self.w * 32,), dtype=torch.float64, device=dev)
+        self.win.zero_()
+        self.hdl = symm.rendezvous(self.win, group)
+        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        assert len(ptrs) == self.w
+        self.ptrs = (ctypes.c_uint64 * self.w)(*ptrs)
+        self.out = torch.zeros((3, ncomp), dtype=torch.float64, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.empty = torch.zeros((1, ncomp), dtype=torch.float64, device=dev)
+        self.seq = 0
+        torch.cuda.synchronize()
+        td.barrier()                      # every window is zeroed before anyone's first store
+
+    def __call__(self, end_err, local_runs):
+        """end_err: CUDA f64 [local_runs, nc] (ignored if local_runs == 0) -> CUDA [3, nc]."""
+        import ctypes
+        self.seq += 1
+        err = end_err if local_runs else self.empty
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._check(self._lib.b2ins_error_stats_exchange_f64(
+            int(local_runs), self.nc, ctypes.c_void_p(err.data_ptr()), self.r, self.w, self.ptrs,
+            self.seq, ctypes.c_void_p(self.out.data_ptr()), ctypes.c_void_p(self.flag.data_ptr()),
+            stream))
+        return self.out
+
+    def timed_out(self):
+        return bool(self.flag.item())
+
+
 def ensemble_stats(end_err, total_runs):
     """[3, ncomp] numpy = max|e|, mean, std over ALL ranks' runs.
     end_err: this rank's CUDA [R_local, ncomp] (or None if it owns no runs)."""

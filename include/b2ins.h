@@ -219,6 +219,20 @@ int b2ins_error_partial2_f64(int64_t runs, int ncomp, const double* err, const d
 int b2ins_error_stats_f64(int64_t runs, int ncomp, const double* err, double* stats,
                           void* workspace, void* stream);
 
+/* ---- K3x: statistics fused with their multi-GPU exchange ----------------------------------
+ * One kernel per rank: shard statistics of err [runs][ncomp] (runs may be 0), peer stores of
+ * (max, mean, std, count) into every rank's window over NVLink, flag exchange, Chan merge ->
+ * stats [3][ncomp] of ALL ranks' runs on every rank.  No NCCL on the data path.
+ *   windows[world]: DEVICE addresses, valid in THIS process, of each rank's receive window
+ *       (rank's own included): 2 * world * 32 doubles of symmetric / peer-mapped memory, zeroed
+ *       once before the first call;  seq: 1, 2, 3, ... per communicator (same on all ranks);
+ *   every rank must make the same sequence of calls.  Needs runs * ncomp <= 2^17 per rank
+ *   (the single-block path) and world <= 16.  timeout_flag: device int, set to 1 if a peer
+ *   did not arrive within ~2 s. */
+int b2ins_error_stats_exchange_f64(int64_t runs, int ncomp, const double* err, int rank, int world,
+                                   const uint64_t* windows, uint64_t seq, double* stats,
+                                   int* timeout_flag, void* stream);
+
 /* ---- K4: Allan variance ---------------------------------------------------
  * Replaces allan.allan_var (allan/allan.py:18-59) for `nseries` series at once.
  * Series s, sample t lives at x[s / inner * outer_stride + (s % inner) + t * sample_stride]

@@ -32,7 +32,20 @@ def _worker(rank, world, port, tmp):
     mine = sim.end_point_errors()
     allrows = dist.gather_rows(torch.from_numpy(mine), 1003)
     ps = sim.get_error_stats('vel', err_stats_start=5.0)
-    np.savez(os.path.join(tmp, 'r%d.npz' % rank), rows=allrows, local=mine.shape[0],
+    # K3x: the fused statistics + peer-memory exchange kernel, twice (double-buffered windows)
+    fused = np.zeros((2, 3, 9))
+    try:
+        p2p = dist.P2PStats(9)
+        dev_err = torch.from_numpy(mine).cuda()
+        fused[0] = p2p(dev_err, mine.shape[0]).cpu().numpy()
+        fused[1] = p2p(dev_err * 2.0, mine.shape[0]).cpu().numpy()
+        assert not p2p.timed_out()
+        fused_ok = 1
+    except Exception as e:          # symmetric memory unavailable on this box
+        sys.stderr.write('P2PStats skipped: %s\n' % e)
+        fused_ok = 0
+    np.savez(os.path.join(tmp, 'r%d.npz' % rank), rows=allrows, local=mine.shape[0], fused=fused,
+             fused_ok=fused_ok,
              proc=np.stack([ps['std']['algo0_%d' % r] for r in (0, 501, 1002)]), **st)
     td.destroy_process_group()
 
@@ -66,6 +79,11 @@ def test_sharded_runs_match_single_gpu(tmp_path):
         assert_close(z['proc'], np.stack([ps['std']['algo0_%d' % i] for i in (0, 501, 1002)]),
                      1e-9, 1e-9, 'process std')
         locals_.append(int(z['local']))
+        if int(z['fused_ok']):
+            full = np.stack([np.abs(rows).max(0), rows.mean(0), rows.std(0)])
+            assert_close(z['fused'][0], full, 1e-11, 1e-12, 'K3x fused exchange')
+            assert_close(z['fused'][1], np.stack([full[0] * 2, full[1] * 2, full[2] * 2]), 1e-11, 1e-12,
+                         'K3x second call')
     assert sorted(locals_) == [501, 502]
     # the first 8 runs are the golden ones
     assert_close(rows[:8, 3:6], g['pos'][:, -1] - g['ref_pos'][-1], 1e-6, 1e-2, 'golden')
