@@ -33,16 +33,18 @@ struct AllanLevelParams {
   int level0;
   double* next;          // S_{k+1} [nseries][next_len]
   double* partial;       // [nseries][chunks][9]
-  int64_t chunks;
+  int64_t chunks;        // chunks per series at this level
   int jmax;              // cluster multipliers 1..jmax are wanted at this level
+  int64_t chunk_first;   // this launch covers chunks [chunk_first, chunk_first + chunk_count)
+  int64_t chunk_count;
 };
 
 __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid_constant__ AllanLevelParams p) {
   extern __shared__ double tile[];  // [kAllanHalo + kAllanChunk + 1] prefix, tile[0] = 0
   __shared__ double red[kAllanThreads / 32][9];
   __shared__ double sh_scan[kAllanThreads];
-  const int64_t series = blockIdx.x / p.chunks;
-  const int64_t chunk = blockIdx.x % p.chunks;
+  const int64_t series = blockIdx.x / p.chunk_count;
+  const int64_t chunk = p.chunk_first + blockIdx.x % p.chunk_count;
   const int64_t c0 = chunk * kAllanChunk;                 // first element of the chunk
   const int halo = (chunk == 0) ? 0 : kAllanHalo;          // elements before c0 in the tile
   const int64_t lo = c0 - halo;
@@ -137,6 +139,150 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
   }
 }
 
+// ---- fast path: FULL chunks ---------------------------------------------------------------
+// A full chunk holds an integer number of clusters of every size (5040 = 2 lcm(1..10)), so the
+// cluster sums can be built hierarchically in registers, a few samples per work item, without
+// any bound checks:
+//   role A (8 samples / item, from a copy padded 8 -> 9 doubles: conflict-free):  j = 1, 2, 4, 8
+//   role B (18 samples / item):  j = 3, 6, 9        role C (10 / item):  j = 5 and the decade sums
+//   role D (7 / item):  j = 7
+// An item also rebuilds the LAST clusters of the samples just before it (at most 9 samples, the
+// halo for item 0) for the difference that straddles its left edge.  ~25 instructions per sample
+// against ~107 of the prefix-sum kernel above, which remains the path for the ragged last chunk.
+constexpr int kAllanPad8 = kAllanChunk / 8 * 9;
+
+__device__ __forceinline__ double sq_acc(double a, double b, double acc) {
+  const double d = a - b;
+  return fma(d, d, acc);
+}
+
+__global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
+  extern __shared__ double smem[];
+  double* raw = smem;                                // [kAllanHalo + kAllanChunk]: raw[h + e]
+  double* pad8 = smem + kAllanHalo + kAllanChunk + 1;  // [kAllanPad8]: element e at e + e/8
+  __shared__ double red[kAllanThreads / 32][9];
+  const int64_t series = blockIdx.x / p.chunk_count;
+  const int64_t chunk = p.chunk_first + blockIdx.x % p.chunk_count;
+  const int64_t c0 = chunk * kAllanChunk;
+  const int h = (chunk == 0) ? 0 : kAllanHalo;
+  const bool has_prev = chunk != 0;
+  const int64_t lo = c0 - h;
+  const double* base;
+  int64_t stride;
+  if (p.level0) {
+    base = p.src + (series / p.inner) * p.outer_stride + (series % p.inner);
+    stride = p.sample_stride;
+  } else {
+    base = p.src + series * p.len;
+    stride = 1;
+  }
+  const double off = base[lo * stride];
+  for (int i = threadIdx.x; i < kAllanChunk + h; i += kAllanThreads) {
+    const double v = base[(lo + i) * stride] - off;
+    raw[i] = v;
+    const int e = i - h;
+    if (e >= 0) pad8[e + (e >> 3)] = v;
+  }
+  __syncthreads();
+  const double* x = raw + h;   // x[e], e in [-h, kAllanChunk)
+  double a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0;
+  const int jm = p.jmax;
+
+  // ---- role A: j = 1, 2, 4, 8 ------------------------------------------------------------
+  for (int it = threadIdx.x; it < kAllanChunk / 8; it += kAllanThreads) {
+    const double* c = pad8 + 9 * it;
+    const double x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], x4 = c[4], x5 = c[5], x6 = c[6], x7 = c[7];
+    const double p0 = x0 + x1, p1 = x2 + x3, p2 = x4 + x5, p3 = x6 + x7;
+    const double q0 = p0 + p1, q1 = p2 + p3;
+    const double r = q0 + q1;
+    a1 = sq_acc(x1, x0, a1); a1 = sq_acc(x2, x1, a1); a1 = sq_acc(x3, x2, a1); a1 = sq_acc(x4, x3, a1);
+    a1 = sq_acc(x5, x4, a1); a1 = sq_acc(x6, x5, a1); a1 = sq_acc(x7, x6, a1);
+    a2 = sq_acc(p1, p0, a2); a2 = sq_acc(p2, p1, a2); a2 = sq_acc(p3, p2, a2);
+    a4 = sq_acc(q1, q0, a4);
+    if (it > 0 || has_prev) {
+      double y[8];
+      if (it > 0) {
+        const double* d = c - 9;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[q] = d[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[q] = x[q - 8];
+      }
+      const double pp2 = y[4] + y[5], pp3 = y[6] + y[7];
+      const double qq1 = pp2 + pp3, qq0 = (y[0] + y[1]) + (y[2] + y[3]);
+      a1 = sq_acc(x0, y[7], a1);
+      a2 = sq_acc(p0, pp3, a2);
+      a4 = sq_acc(q0, qq1, a4);
+      a8 = sq_acc(r, qq0 + qq1, a8);
+    }
+  }
+  // ---- role B: j = 3, 6, 9 -----------------------------------------------------------------
+  if (jm >= 3) {
+    for (int it = threadIdx.x; it < kAllanChunk / 18; it += kAllanThreads) {
+      const double* c = x + 18 * it;
+      double t[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) t[q] = (c[3 * q] + c[3 * q + 1]) + c[3 * q + 2];
+      const double s0 = t[0] + t[1], s1 = t[2] + t[3], s2 = t[4] + t[5];
+      const double n0 = s0 + t[2], n1 = t[3] + s2;
+#pragma unroll
+      for (int q = 1; q < 6; ++q) a3 = sq_acc(t[q], t[q - 1], a3);
+      a6 = sq_acc(s1, s0, a6); a6 = sq_acc(s2, s1, a6);
+      a9 = sq_acc(n1, n0, a9);
+      if (it > 0 || has_prev) {
+        // the clusters that end at the left edge: 3, 6 and 9 samples back
+        const double u2 = (c[-3] + c[-2]) + c[-1], u1 = (c[-6] + c[-5]) + c[-4], u0 = (c[-9] + c[-8]) + c[-7];
+        a3 = sq_acc(t[0], u2, a3);
+        a6 = sq_acc(s0, u1 + u2, a6);
+        a9 = sq_acc(n0, (u0 + u1) + u2, a9);
+      }
+    }
+  }
+  // ---- role C: j = 5 and the decade sums ------------------------------------------------------
+  {
+    const int64_t d_lo = c0 / 10;
+    for (int it = threadIdx.x; it < kAllanChunk / 10; it += kAllanThreads) {
+      const double* c = x + 10 * it;
+      const double f0 = ((c[0] + c[1]) + (c[2] + c[3])) + c[4];
+      const double f1 = ((c[5] + c[6]) + (c[7] + c[8])) + c[9];
+      a5 = sq_acc(f1, f0, a5);
+      if (it > 0 || has_prev) {
+        const double g1 = ((c[-5] + c[-4]) + (c[-3] + c[-2])) + c[-1];
+        a5 = sq_acc(f0, g1, a5);
+      }
+      if (p.next_len > 0) p.next[series * p.next_len + d_lo + it] = (f0 + f1) + 10.0 * off;
+    }
+  }
+  // ---- role D: j = 7 -----------------------------------------------------------------------------
+  if (jm >= 7) {
+    for (int it = threadIdx.x; it < kAllanChunk / 7; it += kAllanThreads) {
+      const double* c = x + 7 * it;
+      const double g = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + c[6]);
+      if (it > 0 || has_prev) {
+        const double gp = ((c[-7] + c[-6]) + (c[-5] + c[-4])) + ((c[-3] + c[-2]) + c[-1]);
+        a7 = sq_acc(g, gp, a7);
+      }
+    }
+  }
+  // ---- block reduction, fixed order -------------------------------------------------------------
+  const double acc[9] = {a1, a2, a3, a4, a5, a6, a7, a8, a9};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double v = 0.0;
+    for (int w = 0; w < kAllanThreads / 32; ++w) v += red[w][threadIdx.x];
+    p.partial[(series * p.chunks + chunk) * 9 + threadIdx.x] = (threadIdx.x < jm) ? v : 0.0;
+  }
+}
+
 struct AllanFinalParams {
   int64_t nseries;
   int ntau;
@@ -214,10 +360,14 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
   double* part = ws + 2 * n1 * nseries;
   int64_t len = n;
   const size_t smem = (kAllanChunk + kAllanHalo + 1 + 16) * sizeof(double);
+  const size_t smem_full = (kAllanChunk + kAllanHalo + 1 + kAllanPad8 + 16) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(allan_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem)) != cudaSuccess)
+      return 2;
+    if (cudaFuncSetAttribute(allan_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_full)) != cudaSuccess)
       return 2;
     attr_set = true;
   }
@@ -239,7 +389,18 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     fp.chunks[k] = lp.chunks;
     part += lp.chunks * 9 * nseries;
     if (lp.chunks * nseries >= (int64_t(1) << 31)) return 4;
-    allan_level_kernel<<<static_cast<unsigned>(lp.chunks * nseries), kAllanThreads, smem, s>>>(lp);
+    // full chunks (every cluster complete, next-level decades complete) take the fast kernel
+    const int64_t full = len / kAllanChunk;
+    if (full > 0) {
+      lp.chunk_first = 0;
+      lp.chunk_count = full;
+      allan_full_kernel<<<static_cast<unsigned>(full * nseries), kAllanThreads, smem_full, s>>>(lp);
+    }
+    if (lp.chunks > full) {   // the ragged last chunk
+      lp.chunk_first = full;
+      lp.chunk_count = lp.chunks - full;
+      allan_level_kernel<<<static_cast<unsigned>(lp.chunk_count * nseries), kAllanThreads, smem, s>>>(lp);
+    }
     len /= 10;
   }
   const int64_t total = nseries * ntau;

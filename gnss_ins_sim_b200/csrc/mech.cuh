@@ -61,6 +61,27 @@ __device__ __forceinline__ Vec3 mul_t(const Dcm& c, const Vec3& v) {  // c^T . v
   return Vec3{c.c00 * v.x + c.c10 * v.y + c.c20 * v.z, c.c01 * v.x + c.c11 * v.y + c.c21 * v.z,
               c.c02 * v.x + c.c12 * v.y + c.c22 * v.z};
 }
+// c_bn^T . v and c_bn . v without forming the matrix: the ZYX dcm is Rx(roll) Ry(pitch) Rz(yaw),
+// so each product is three planar rotations (12 multiply-adds instead of 16 + 9).  Same value as
+// dcm_from_sincos + mul / mul_t up to rounding.
+__device__ __forceinline__ Vec3 rot_b2n(const SinCos3& t, const Vec3& v) {   // c^T . v
+  // undo roll (about x)
+  const double y1 = t.cr * v.y - t.sr * v.z;
+  const double z1 = t.sr * v.y + t.cr * v.z;
+  // undo pitch (about y)
+  const double x2 = t.cp * v.x + t.sp * z1;
+  const double z2 = -t.sp * v.x + t.cp * z1;
+  // undo yaw (about z)
+  return Vec3{t.cy * x2 - t.sy * y1, t.sy * x2 + t.cy * y1, z2};
+}
+__device__ __forceinline__ Vec3 rot_n2b(const SinCos3& t, const Vec3& v) {   // c . v
+  const double x1 = t.cy * v.x + t.sy * v.y;
+  const double y1 = -t.sy * v.x + t.cy * v.y;
+  const double x2 = t.cp * x1 - t.sp * v.z;
+  const double z2 = t.sp * x1 + t.cp * v.z;
+  return Vec3{x2, t.cr * y1 + t.sr * z2, -t.sr * y1 + t.cr * z2};
+}
+
 // attitude.cross3: attitude.py:758-770
 __device__ __forceinline__ Vec3 cross3(const Vec3& a, const Vec3& b) {
   return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
@@ -223,8 +244,7 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
       s.vel_b.z = s.vel_b.z + (accel.z + cg.z) * dt - wxv.z * dt;
     }
     refresh_trig<RF, SPLIT>(s, role);
-    const Dcm c = dcm_from_sincos(s.sc);
-    s.vel = mul_t(c, s.vel_b);
+    s.vel = rot_b2n(s.sc, s.vel_b);
     s.pos.x += vel_old.x * dt;
     s.pos.y += vel_old.y * dt;
     s.pos.z += vel_old.z * dt;
@@ -241,11 +261,10 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
       w_ie.x = kWie * p.cl;
       w_ie.z = -kWie * p.sl;
     }
-    const Dcm c = dcm_from_sincos(s.sc);  // c_bn of step i-1
     const Vec3 w_sum{w_en.x + w_ie.x, w_en.y + w_ie.y, w_en.z + w_ie.z};
-    const Vec3 cw = mul(c, w_sum);
+    const Vec3 cw = rot_n2b(s.sc, w_sum);   // c_bn of step i-1
     const Vec3 w_nb{gyro.x - cw.x, gyro.y - cw.y, gyro.z - cw.z};
-    const Vec3 fa = mul_t(c, accel);
+    const Vec3 fa = rot_b2n(s.sc, accel);
     const Vec3 w2{2 * w_ie.x + w_en.x, 2 * w_ie.y + w_en.y, 2 * w_ie.z + w_en.z};
     const Vec3 cor = cross3(w2, s.vel);
     const Vec3 vel_old = s.vel;
@@ -255,8 +274,7 @@ __device__ __forceinline__ void nav_step(NavState& s, const Vec3& gyro, const Ve
     s.pos.z += (-vel_old.z) * dt;
     refresh_trig<RF, SPLIT>(s, role);
     if (odo) {
-      const Dcm cn = dcm_from_sincos(s.sc);   // c_bn of step i
-      s.vel = mul_t(cn, Vec3{accel.x, 0.0, 0.0});
+      s.vel = rot_b2n(s.sc, Vec3{accel.x, 0.0, 0.0});   // c_bn of step i
     } else {
       s.vel.x = vel_old.x + (fa.x - cor.x) * dt;
       s.vel.y = vel_old.y + (fa.y - cor.y) * dt;
