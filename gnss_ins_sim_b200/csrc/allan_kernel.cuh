@@ -177,11 +177,26 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
     stride = 1;
   }
   const double off = base[lo * stride];
-  for (int i = threadIdx.x; i < kAllanChunk + h; i += kAllanThreads) {
-    const double v = base[(lo + i) * stride] - off;
-    raw[i] = v;
-    const int e = i - h;
-    if (e >= 0) pad8[e + (e >> 3)] = v;
+  {
+    // all the loads of a thread are issued before the first use: 20 independent requests in flight
+    // per thread instead of a load -> store chain that exposes the DRAM latency 20 times
+    constexpr int kPer = (kAllanChunk + kAllanHalo + kAllanThreads - 1) / kAllanThreads;
+    double v[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = threadIdx.x + q * kAllanThreads;
+      v[q] = (i < kAllanChunk + h) ? base[(lo + i) * stride] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = threadIdx.x + q * kAllanThreads;
+      if (i < kAllanChunk + h) {
+        const double w = v[q] - off;
+        raw[i] = w;
+        const int e = i - h;
+        if (e >= 0) pad8[e + (e >> 3)] = w;
+      }
+    }
   }
   __syncthreads();
   const double* x = raw + h;   // x[e], e in [-h, kAllanChunk)

@@ -438,8 +438,8 @@ mc_kernel(const __grid_constant__ McParams p) {
       // samples of this block that are followed by a step (the last sample of the series is not)
       const int kmax = static_cast<int>(min64(min64(G, cnt - base), p.n - 1 - (t0 + base)));
       const SampleSlot* grp = &sm.slot[warp][lane - j];
-#pragma unroll 1
-      for (int k = 0; k < kmax; ++k) {
+      // One step of the recurrence; HIST keeps the state after sample base+k in lane k.
+      auto one_step = [&](int k, bool hist) {
         Vec3 w, f;
         if (G == 1) {
           w = Vec3{mg[0], mg[1], mg[2]};
@@ -455,11 +455,25 @@ mc_kernel(const __grid_constant__ McParams p) {
             proc_accumulate(st, &sm.nav[s][(base + k) * 9], pe_max, pe_sum, pe_sq, pe_k, pe_cnt);
         }
         nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role, odo_mode);
-        if (warp_dumps && j == k) {
+        if (hist && j == k) {
           keep[0] = st.yaw; keep[1] = st.pitch; keep[2] = st.roll;
           keep[3] = st.pos.x; keep[4] = st.pos.y; keep[5] = st.pos.z;
           keep[6] = st.vel.x; keep[7] = st.vel.y; keep[8] = st.vel.z;
         }
+      };
+      if (warp_dumps) {            // history output: the rare path keeps the simple loop
+#pragma unroll 1
+        for (int k = 0; k < kmax; ++k) one_step(k, true);
+      } else {
+        // two steps per iteration: the off-chain tail of step k (velocity, position) overlaps the
+        // dependency chain of step k+1 (ptxas does not pipeline across iterations by itself)
+        int k = 0;
+#pragma unroll 1
+        for (; k + 1 < kmax; k += 2) {
+          one_step(k, false);
+          one_step(k + 1, false);
+        }
+        if (k < kmax) one_step(k, false);
       }
       if (G > 1) __syncwarp();   // slots are rewritten by the next block
       B2_CLK(cb1);
