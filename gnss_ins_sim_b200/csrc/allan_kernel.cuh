@@ -150,17 +150,18 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
 // halo for item 0) for the difference that straddles its left edge.  ~25 instructions per sample
 // against ~107 of the prefix-sum kernel above, which remains the path for the ragged last chunk.
 constexpr int kAllanPad8 = kAllanChunk / 8 * 9;
+constexpr int kAllanFullThreads = 512;   // two 86 KB CTAs per SM: 32 warps to hide the load latency
 
 __device__ __forceinline__ double sq_acc(double a, double b, double acc) {
   const double d = a - b;
   return fma(d, d, acc);
 }
 
-__global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
+__global__ void __launch_bounds__(kAllanFullThreads) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
   extern __shared__ double smem[];
   double* raw = smem;                                // [kAllanHalo + kAllanChunk]: raw[h + e]
   double* pad8 = smem + kAllanHalo + kAllanChunk + 1;  // [kAllanPad8]: element e at e + e/8
-  __shared__ double red[kAllanThreads / 32][9];
+  __shared__ double red[kAllanFullThreads / 32][9];
   const int64_t series = blockIdx.x / p.chunk_count;
   const int64_t chunk = p.chunk_first + blockIdx.x % p.chunk_count;
   const int64_t c0 = chunk * kAllanChunk;
@@ -180,16 +181,16 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
   {
     // all the loads of a thread are issued before the first use: 20 independent requests in flight
     // per thread instead of a load -> store chain that exposes the DRAM latency 20 times
-    constexpr int kPer = (kAllanChunk + kAllanHalo + kAllanThreads - 1) / kAllanThreads;
+    constexpr int kPer = (kAllanChunk + kAllanHalo + kAllanFullThreads - 1) / kAllanFullThreads;
     double v[kPer];
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
-      const int i = threadIdx.x + q * kAllanThreads;
+      const int i = threadIdx.x + q * kAllanFullThreads;
       v[q] = (i < kAllanChunk + h) ? base[(lo + i) * stride] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
-      const int i = threadIdx.x + q * kAllanThreads;
+      const int i = threadIdx.x + q * kAllanFullThreads;
       if (i < kAllanChunk + h) {
         const double w = v[q] - off;
         raw[i] = w;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
   const int jm = p.jmax;
 
   // ---- role A: j = 1, 2, 4, 8 ------------------------------------------------------------
-  for (int it = threadIdx.x; it < kAllanChunk / 8; it += kAllanThreads) {
+  for (int it = threadIdx.x; it < kAllanChunk / 8; it += kAllanFullThreads) {
     const double* c = pad8 + 9 * it;
     const double x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], x4 = c[4], x5 = c[5], x6 = c[6], x7 = c[7];
     const double p0 = x0 + x1, p1 = x2 + x3, p2 = x4 + x5, p3 = x6 + x7;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
   }
   // ---- role B: j = 3, 6, 9 -----------------------------------------------------------------
   if (jm >= 3) {
-    for (int it = threadIdx.x; it < kAllanChunk / 18; it += kAllanThreads) {
+    for (int it = threadIdx.x; it < kAllanChunk / 18; it += kAllanFullThreads) {
       const double* c = x + 18 * it;
       double t[6];
 #pragma unroll
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
   // ---- role C: j = 5 and the decade sums ------------------------------------------------------
   {
     const int64_t d_lo = c0 / 10;
-    for (int it = threadIdx.x; it < kAllanChunk / 10; it += kAllanThreads) {
+    for (int it = threadIdx.x; it < kAllanChunk / 10; it += kAllanFullThreads) {
       const double* c = x + 10 * it;
       const double f0 = ((c[0] + c[1]) + (c[2] + c[3])) + c[4];
       const double f1 = ((c[5] + c[6]) + (c[7] + c[8])) + c[9];
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
   }
   // ---- role D: j = 7 -----------------------------------------------------------------------------
   if (jm >= 7) {
-    for (int it = threadIdx.x; it < kAllanChunk / 7; it += kAllanThreads) {
+    for (int it = threadIdx.x; it < kAllanChunk / 7; it += kAllanFullThreads) {
       const double* c = x + 7 * it;
       const double g = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + c[6]);
       if (it > 0 || has_prev) {
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_full_kernel(const __grid_
   __syncthreads();
   if (threadIdx.x < 9) {
     double v = 0.0;
-    for (int w = 0; w < kAllanThreads / 32; ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < kAllanFullThreads / 32; ++w) v += red[w][threadIdx.x];
     p.partial[(series * p.chunks + chunk) * 9 + threadIdx.x] = (threadIdx.x < jm) ? v : 0.0;
   }
 }
@@ -409,7 +410,7 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     if (full > 0) {
       lp.chunk_first = 0;
       lp.chunk_count = full;
-      allan_full_kernel<<<static_cast<unsigned>(full * nseries), kAllanThreads, smem_full, s>>>(lp);
+      allan_full_kernel<<<static_cast<unsigned>(full * nseries), kAllanFullThreads, smem_full, s>>>(lp);
     }
     if (lp.chunks > full) {   // the ragged last chunk
       lp.chunk_first = full;

@@ -12,6 +12,7 @@
 #include "allan_kernel.cuh"
 #include "mc_kernel.cuh"
 #include "noise_kernel.cuh"
+#include "pathgen_host.h"
 #include "psd_kernel.cuh"
 #include "stats_kernel.cuh"
 
@@ -793,6 +794,25 @@ int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int tab
   psd_synth_kernel<<<g2, kPsdThreads, 0, s>>>(p);
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
+}
+
+// ---------------------------------------------------------------- host ------
+int64_t b2ins_path_rows(const double* motion_def, int64_t segs, double fs) {
+  if (!motion_def || segs <= 0 || !(fs > 0.0)) return -1;
+  return b2ins_host::path_rows(motion_def, segs, fs);
+}
+
+int64_t b2ins_path_gen_host(const double* ini, const double* motion_def, int64_t segs, double fs,
+                            double osr, double fs_gps, double fs_odo, const double* mobility,
+                            int ref_frame, int64_t cap, double* imu, double* nav, double* gps,
+                            int64_t* gps_rows, double* odo) {
+  if (!ini || !motion_def || !mobility || !imu || !nav || segs <= 0 || !(fs > 0.0) || !(osr >= 1.0) ||
+      (ref_frame != 0 && ref_frame != 1) || (gps && !(fs_gps > 0.0))) {
+    fail(B2INS_ERR_ARG, "bad argument to b2ins_path_gen_host");
+    return -1;
+  }
+  return b2ins_host::path_gen(ini, motion_def, segs, fs, osr, fs_gps, fs_odo, mobility, ref_frame,
+                              cap, imu, nav, gps, gps_rows, odo);
 }
 
 // ---------------------------------------------------------------- diag ------

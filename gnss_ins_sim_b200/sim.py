@@ -7,9 +7,9 @@ What stays on the CPU, by design (BASELINE north_star: "pathgen.path_gen stays C
 and its reference trajectory is broadcast once"): the true trajectory.  `motion_def` is
   * a trajectory: dict / .npz path with time, ref_pos, ref_vel, ref_att, ref_accel,
     ref_gyro (what pathgen.path_gen returns, e.g. tests/golden/traj_*.npz), or
-  * a motion-definition .csv / string exactly as the reference takes it; it is turned
-    into a trajectory by gnss_ins_sim.pathgen.path_gen, which therefore has to be
-    importable (pip install gnss-ins-sim); nothing else of the reference is used.
+  * a motion-definition .csv / string exactly as the reference takes it; it is turned into a
+    trajectory on the host by gnss_ins_sim_b200.pathgen.path_gen (C++ restatement of the
+    reference's path generator, identical output, ~200x faster).
 
 Dispatch on `algorithm`:
   * gnss_ins_sim_b200 FreeIntegration  -> K12, the fused noise+integration+error kernel;
@@ -160,49 +160,30 @@ def load_trajectory(src):
     return out
 
 
-def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetometer=False, odo=False):
-    """Motion-definition csv/string -> trajectory via the reference's CPU path generator
-    (pathgen.path_gen, pathgen.py:26-329), driven exactly as Sim.__gen_data_from_pathgen
-    does (ins_sim.py:444-472, :578-640)."""
-    try:
-        from gnss_ins_sim.pathgen import pathgen
-    except ImportError:
-        raise RuntimeError(
-            'motion_def is a motion-definition file: generating the true trajectory needs '
-            'gnss_ins_sim.pathgen.path_gen (CPU side, out of scope of this engine). Install '
-            'gnss-ins-sim or pass a precomputed trajectory (dict / .npz) as motion_def.')
-    try:
-        if os.path.isfile(motion_def):
-            ini = np.genfromtxt(motion_def, delimiter=',', skip_header=1, max_rows=1)
-            way = np.genfromtxt(motion_def, delimiter=',', skip_header=3)
-        else:
-            from io import StringIO
-            ini = np.genfromtxt(StringIO(motion_def), delimiter=',', skip_header=1, max_rows=1)
-            way = np.genfromtxt(StringIO(motion_def), delimiter=',', skip_header=3)
-    except Exception:
-        raise ValueError('motion definition file/string must have nine columns '
-                         'and four rows at least (two header rows + at least two data rows).')
-    if way.ndim == 1:
-        way = way.reshape((1, len(way)))
-    ini_pva = ini[:9].astype(np.float64)
-    cmd = way[:, :9].astype(np.float64)
-    ini_pva[0:2] *= D2R
-    ini_pva[6:9] *= D2R
-    cmd[:, 1:4] *= D2R
-    cmd[np.isnan(cmd)] = 0.0
-    if mode is None:
-        mobility = np.array([1.0, 0.5, 2.0])      # 'high_mobility', ins_sim.py:612-640
-    else:
-        mobility = np.array(mode, dtype=np.float64)
-        mobility[1:3] = mobility[1:3] * D2R
-    output_def = np.array([[1.0, fs], [-1.0, fs], [1.0 if odo else -1.0, fs]])
+def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetometer=False, odo=False,
+                               gps=False, fs_gps=0.0):
+    """Motion-definition csv/string -> trajectory dict, driven exactly as
+    Sim.__gen_data_from_pathgen does (ins_sim.py:444-472): parse (ins_sim.py:578-640), then
+    path_gen -- here the host-side restatement in csrc/pathgen_host.h (pathgen.py), ~200x faster
+    than the reference's Python loop and identical to it to the last bits."""
+    from . import pathgen
+    ini_pva, cmd = pathgen.parse_motion(motion_def)
+    mobility = pathgen.parse_mode(mode)
+    output_def = np.array([[1.0, fs], [1.0 if gps else -1.0, fs_gps if gps else fs],
+                           [1.0 if odo else -1.0, fs]])
     rtn = pathgen.path_gen(ini_pva, cmd, output_def, mobility, ref_frame, magnetometer)
-    extra = {'ref_odo': np.ascontiguousarray(rtn['odo'][:, 2])} if odo else {}
-    return dict(extra, **{'time': rtn['nav'][:, 0] / fs, 'ref_pos': np.ascontiguousarray(rtn['nav'][:, 1:4]),
-            'ref_vel': np.ascontiguousarray(rtn['nav'][:, 4:7]),
-            'ref_att': np.ascontiguousarray(rtn['nav'][:, 7:10]),
-            'ref_accel': np.ascontiguousarray(rtn['imu'][:, 1:4]),
-            'ref_gyro': np.ascontiguousarray(rtn['imu'][:, 4:7]), 'ini': ini_pva})
+    out = {'time': rtn['nav'][:, 0] / fs, 'ref_pos': np.ascontiguousarray(rtn['nav'][:, 1:4]),
+           'ref_vel': np.ascontiguousarray(rtn['nav'][:, 4:7]),
+           'ref_att': np.ascontiguousarray(rtn['nav'][:, 7:10]),
+           'ref_accel': np.ascontiguousarray(rtn['imu'][:, 1:4]),
+           'ref_gyro': np.ascontiguousarray(rtn['imu'][:, 4:7]), 'ini': ini_pva}
+    if odo:
+        out['ref_odo'] = np.ascontiguousarray(rtn['odo'][:, 2])
+    if gps:
+        out['gps_time'] = rtn['gps'][:, 0] / fs
+        out['ref_gps'] = np.ascontiguousarray(rtn['gps'][:, 1:7])
+        out['gps_visibility'] = np.ascontiguousarray(rtn['gps'][:, 7])
+    return out
 
 
 class LazyRuns(Mapping):
@@ -322,7 +303,9 @@ class Sim(object):
                     'FreeIntegration.run_batch / Allan.run_batch instead')
             traj = trajectory_from_motion_def(self.fs[0], src, self.ref_frame, self.mode,
                                               bool(self.imu and self.imu.magnetometer),
-                                              bool(self.imu and self.imu.odo))
+                                              bool(self.imu and self.imu.odo),
+                                              bool(self.imu and self.imu.gps) and self.fs[1] > 0,
+                                              self.fs[1])
         else:
             raise TypeError('motion_def must be a trajectory dict, an .npz path or a motion '
                             'definition csv/string')
@@ -335,8 +318,9 @@ class Sim(object):
         d['ref_pos'], d['ref_vel'], d['ref_att_euler'] = traj['ref_pos'], traj['ref_vel'], traj['ref_att']
         d['ref_accel'], d['ref_gyro'] = traj['ref_accel'], traj['ref_gyro']
         d['ref_att_quat'] = euler2quat_zyx(traj['ref_att'])
-        if 'ref_odo' in traj:
-            d['ref_odo'] = traj['ref_odo']
+        for k in ('ref_odo', 'gps_time', 'ref_gps', 'gps_visibility'):
+            if k in traj:
+                d[k] = traj[k]
         self._nav_end = np.concatenate([traj['ref_att'][-1], traj['ref_pos'][-1], traj['ref_vel'][-1]])
         self._nav_cache = None
         self._dev_cache = None

@@ -261,6 +261,26 @@ int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int tab
                          const double* freq, const double* sxx3, uint64_t seed,
                          int64_t run_offset, double* series, void* workspace, void* stream);
 
+/* ---- host: true-trajectory generator -----------------------------------------------
+ * Replaces pathgen.path_gen (gnss_ins_sim/pathgen/pathgen.py:26-329, with
+ * calc_true_sensor_output :331-411 and parse_motion_def :413-439).  Plain CPU code (the
+ * trajectory is generated once, serially in time, and shared by all runs); no GPU needed.
+ *   ini [9]: lat, lon [rad], alt, body velocity, yaw, pitch, roll [rad];
+ *   motion_def [segs][9]: type, 3 attitude commands [rad | rad/s], 3 velocity commands, duration
+ *       [s], gps visibility -- as Sim.__parse_motion produces them (ins_sim.py:578-610);
+ *   mobility [3]: max acceleration, max angular acceleration [rad/s^2], max angular rate [rad/s];
+ *   fs: IMU rate; osr: simulation over-sampling ratio (1); fs_gps, fs_odo: only used if the
+ *       matching output buffer is given.
+ *   imu [cap][7] (index, accel xyz, gyro xyz), nav [cap][10] (index, pos, vel NED, yaw pitch roll),
+ *   gps [cap][8] (nullable), odo [cap][5] (nullable).  cap >= b2ins_path_rows(...).
+ * Returns the number of imu/nav rows written, or < 0: -2 negative duration, -3 empty, -4 cap too
+ * small, -5 unknown command type.  Magnetometer output is not generated. */
+int64_t b2ins_path_rows(const double* motion_def, int64_t segs, double fs);
+int64_t b2ins_path_gen_host(const double* ini, const double* motion_def, int64_t segs, double fs,
+                            double osr, double fs_gps, double fs_odo, const double* mobility,
+                            int ref_frame, int64_t cap, double* imu, double* nav, double* gps,
+                            int64_t* gps_rows, double* odo);
+
 /* ---- diagnostics ---------------------------------------------------------
  * Measured FP64 FMA issue rate of the current device [lane-FMA/s]: a ~10 ms dependent-chain
  * microbenchmark (8 independent chains per thread, every SM filled).  The Monte-Carlo

@@ -254,6 +254,35 @@ def gen_traj(tag, motion, fs, ref_frame):
                         ref_accel=d.ref_accel.data, ref_gyro=d.ref_gyro.data)
 
 
+def gen_pathgen():
+    """pathgen.path_gen outputs (strided rows + column checksums) for three motion definitions,
+    and the motion-definition files themselves as input fixtures (tests/golden/motion_def*.csv)."""
+    import shutil
+    out = {}
+    for tag, name, fs, rf, gps, odo, stride in (('3d', 'motion_def-3d.csv', 100.0, 0, True, True, 7),
+                                                ('full', 'motion_def.csv', 50.0, 1, False, True, 31),
+                                                ('long_drive', 'motion_def-long_drive.csv', 200.0, 0,
+                                                 True, False, 997)):
+        shutil.copy(os.path.join(MOTION, name), os.path.join(OUT, name))
+        sim = ins_sim.Sim([fs, 10.0, 0.0], os.path.join(MOTION, name), ref_frame=rf,
+                          imu=fresh_imu('low-accuracy'), algorithm=None)
+        ini, cmd = sim._Sim__parse_motion()
+        od = np.array([[1.0, fs], [1.0 if gps else -1.0, 10.0], [1.0 if odo else -1.0, fs]])
+        r = pathgen.path_gen(ini, cmd, od, np.array([1.0, 0.5, 2.0]), rf, False)
+        n = r['nav'].shape[0]
+        idx = np.unique(np.concatenate([np.arange(0, n, stride), [n - 1]]))
+        out.update({tag + '_n': n, tag + '_idx': idx, tag + '_fs': fs, tag + '_rf': rf,
+                    tag + '_imu': r['imu'][idx], tag + '_nav': r['nav'][idx],
+                    tag + '_imu_sum': r['imu'].sum(0), tag + '_nav_abs_sum': np.abs(r['nav']).sum(0)})
+        if gps:
+            out[tag + '_gps'] = r['gps'][::max(1, stride // 10)]
+            out[tag + '_gps_n'] = r['gps'].shape[0]
+        if odo:
+            out[tag + '_odo'] = r['odo'][idx]
+    shutil.copy(os.path.join(MOTION, 'motion_def-90deg_turn.csv'), os.path.join(OUT, 'motion_def-90deg_turn.csv'))
+    np.savez_compressed(os.path.join(OUT, 'pathgen.npz'), **out)
+
+
 def gen_allan():
     rng = np.random.RandomState(2024)
     fs = 100.0
@@ -316,6 +345,7 @@ def main():
     gen_philox_odo(0)
     gen_traj('90deg_turn_100hz_rf1', 'motion_def-90deg_turn.csv', 100.0, 1)
     gen_traj('90deg_turn_100hz_rf0', 'motion_def-90deg_turn.csv', 100.0, 0)
+    gen_pathgen()
     gen_allan()
     gen_psd()
     for f in sorted(os.listdir(OUT)):

@@ -324,3 +324,56 @@ def test_two_rank_statistics_over_gloo(tmp_path):
                      'one-collective merge')
         gyro0 = z['gyro'] if gyro0 is None else gyro0
         assert np.array_equal(z['gyro'], gyro0) and z['gyro'].shape == (50, 3)
+
+
+# ------------------------------------------------------------------ path_gen (host) ---
+def test_path_gen_matches_reference_trajectories():
+    """gnss_ins_sim_b200.pathgen.path_gen (C++ on the host) against rows and column checksums of
+    the reference's pathgen.path_gen for three motion definitions (all five command types, GPS
+    and odometer outputs, both frames, up to 193 036 samples)."""
+    from gnss_ins_sim_b200 import pathgen as pg
+    g = load_golden('pathgen.npz')
+    for tag, name, gps, odo in (('3d', 'motion_def-3d.csv', True, True),
+                                ('full', 'motion_def.csv', False, True),
+                                ('long_drive', 'motion_def-long_drive.csv', True, False)):
+        fs, rf = float(g[tag + '_fs']), int(g[tag + '_rf'])
+        ini, cmd = pg.parse_motion(os.path.join(ROOT, 'tests', 'golden', name))
+        cmd0 = cmd.copy()
+        od = np.array([[1.0, fs], [1.0 if gps else -1.0, 10.0], [1.0 if odo else -1.0, fs]])
+        r = pg.path_gen(ini, cmd, od, pg.HIGH_MOBILITY, rf)
+        assert np.array_equal(cmd, cmd0)                      # inputs are not modified
+        assert r['nav'].shape == (int(g[tag + '_n']), 10) and r['status'] is True
+        idx = g[tag + '_idx']
+        assert_close(r['imu'][idx], g[tag + '_imu'], 1e-12, 1e-3, 'imu rows')
+        assert_close(r['nav'][idx], g[tag + '_nav'], 1e-13, 1e-3, 'nav rows')
+        assert_close(r['imu'].sum(0), g[tag + '_imu_sum'], 1e-11, 1.0, 'imu checksum')
+        assert_close(np.abs(r['nav']).sum(0), g[tag + '_nav_abs_sum'], 1e-12, 1.0, 'nav checksum')
+        if gps:
+            assert r['gps'].shape[0] == int(g[tag + '_gps_n'])
+            assert_close(r['gps'][::max(1, (idx[1] - idx[0]) // 10)], g[tag + '_gps'], 1e-13, 1e-3, 'gps')
+        if odo:
+            assert_close(r['odo'][idx], g[tag + '_odo'], 1e-13, 1e-3, 'odo')
+
+
+def test_path_gen_reproduces_the_bench_trajectory_and_errors():
+    from gnss_ins_sim_b200 import pathgen as pg
+    from gnss_ins_sim_b200.sim import trajectory_from_motion_def
+    for rf in (0, 1):
+        g = load_golden('traj_90deg_turn_100hz_rf%d.npz' % rf)
+        t = trajectory_from_motion_def(100.0, os.path.join(ROOT, 'tests', 'golden', 'motion_def-90deg_turn.csv'),
+                                       rf)
+        for k in ('ref_pos', 'ref_vel', 'ref_att', 'ref_accel', 'ref_gyro', 'time'):
+            assert_close(t[k], g[k], 1e-13, 1e-6, k)
+        assert_close(t['ini'], g['ini'], 0.0, 0.0, 'ini')
+    text = ('ini lat (deg),ini lon (deg),ini alt (m),vx,vy,vz,yaw,pitch,roll\n32,120,0,0,0,0,0,0,0\n'
+            'command type,yaw,pitch,roll,vx,vy,vz,duration,GPS\n1,0,0,0,0,0,0,2,0\n')
+    t = trajectory_from_motion_def(100.0, text, 0, mode=np.array([1.0, 30.0, 60.0]))
+    assert t['ref_gyro'].shape == (200, 3)
+    with pytest.raises(ValueError):
+        pg.path_gen(np.zeros(9), np.array([[1, 0, 0, 0, 0, 0, 0, -1.0, 0]]),
+                    np.array([[1.0, 100.0], [-1.0, 100.0], [-1.0, 100.0]]), pg.HIGH_MOBILITY)
+    with pytest.raises(NotImplementedError):
+        pg.path_gen(np.zeros(9), np.array([[1, 0, 0, 0, 0, 0, 0, 1.0, 0]]),
+                    np.array([[1.0, 100.0], [-1.0, 100.0], [-1.0, 100.0]]), pg.HIGH_MOBILITY, magnet=True)
+    with pytest.raises(TypeError):
+        pg.parse_mode(np.zeros(4))

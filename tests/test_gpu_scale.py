@@ -165,3 +165,32 @@ def test_config4_length_allan_through_sim(eng):
     for r in range(R):
         ratio = adg['algo0_%d' % r][k, :] / (arw / np.sqrt(t[k]))[:, None]
         assert (np.abs(ratio - 1) < 0.05).all()
+
+
+def test_config3_true_long_drive_through_sim(eng):
+    """BASELINE config 3 end to end on its true trajectory: motion_def-long_drive.csv @200 Hz
+    (193 036 samples from the host path generator), 'low-accuracy' IMU, ref_frame 0, through Sim;
+    a handful of runs against the C oracle."""
+    import os
+    from conftest import ROOT
+    from gnss_ins_sim_b200 import imu_model, pathgen
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    csv = os.path.join(ROOT, 'tests', 'golden', 'motion_def-long_drive.csv')
+    ini, _ = pathgen.parse_motion(csv)
+    imu = imu_model.IMU(accuracy='low-accuracy', axis=6, gps=False)
+    sim = Sim([200.0, 0.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=FreeIntegration(ini), seed=11)
+    R = 5
+    sim.run(R)
+    t = sim._traj
+    assert t['ref_gyro'].shape == (193036, 3)
+    nav_end = np.concatenate([t['ref_att'][-1], t['ref_pos'][-1], t['ref_vel'][-1]])
+    o_err, _ = oracle_c.mc_free_integration(0, 200.0, R, 0, t['ref_gyro'], t['ref_accel'], nav_end,
+                                            imu.gyro_err, imu.accel_err, 11, ini[None], threads=0)
+    err = sim.end_point_errors()
+    assert_close(err[:, 0:3], o_err[:, 0:3], 1e-6, 1.0, 'att')
+    assert_close(err[:, 6:9], o_err[:, 6:9], 1e-6, 1.0, 'vel')
+    assert_close(err[:, 3:5] * 6.4e6, o_err[:, 3:5] * 6.4e6, 1e-6, 1.0, 'lat/lon [m]')
+    assert_close(err[:, 5], o_err[:, 5], 1e-6, 1.0, 'alt')
+    st = sim.get_error_stats('pos', -1, extra_opt='ned')
+    assert st['units'] == "['m', 'm', 'm']" and np.isfinite(st['std']).all()
