@@ -350,8 +350,41 @@ int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gy
   p.out_accel = accel;
   layout_strides(layout, runs, n, &p.osr, &p.ost, &p.osc);
   p.z_dump = z_dump;
-  imu_noise_kernel<<<static_cast<unsigned>(runs), kNoiseThreads, 0,
-                     static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Few runs and a long series (the Allan configuration): split the time axis into segments so
+  // that every SM has work.  The Gauss-Markov state at a segment start needs the draws before it:
+  // pass 1 reduces every segment to its zero-state end value, a tiny serial kernel chains them,
+  // pass 0 regenerates (counter-based Philox: nothing is stored) and writes.  Costs the noise
+  // twice, so it is only used when one CTA per run would leave most of the GPU idle.
+  int nseg = 1;
+  const int64_t want_ctas = static_cast<int64_t>(sm_count()) * 2;
+  if (runs < want_ctas && n >= (int64_t(1) << 18)) {
+    nseg = static_cast<int>((want_ctas + runs - 1) / runs);
+    const int64_t max_seg = n / (int64_t(1) << 16);
+    if (nseg > max_seg) nseg = static_cast<int>(max_seg);
+    if (nseg < 1) nseg = 1;
+  }
+  p.nseg = nseg;
+  p.seg_len = n;
+  p.pass = 0;
+  p.seg_carry = nullptr;
+  p.seg_end = nullptr;
+  double* scratch = nullptr;
+  if (nseg > 1) {
+    int64_t len = (n + nseg - 1) / nseg;
+    len = (len + kNoiseThreads - 1) / kNoiseThreads * kNoiseThreads;   // whole tiles per segment
+    p.seg_len = len;
+    p.nseg = static_cast<int>((n + len - 1) / len);
+    CU_CHECK(cudaMallocAsync(&scratch, sizeof(double) * runs * p.nseg * 12, s));
+    p.seg_end = scratch;
+    p.seg_carry = scratch + runs * p.nseg * 6;
+    p.pass = 1;
+    imu_noise_kernel<<<static_cast<unsigned>(runs * p.nseg), kNoiseThreads, 0, s>>>(p);
+    noise_carry_kernel<<<static_cast<unsigned>((runs * 6 + 127) / 128), 128, 0, s>>>(p);
+    p.pass = 0;
+  }
+  imu_noise_kernel<<<static_cast<unsigned>(runs * p.nseg), kNoiseThreads, 0, s>>>(p);
+  if (scratch) CU_CHECK(cudaFreeAsync(scratch, s));
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }

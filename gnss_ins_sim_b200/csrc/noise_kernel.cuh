@@ -23,6 +23,15 @@ struct NoiseParams {
   double* out_accel;
   int64_t osr, ost, osc;
   double* z_dump;  // [runs][n][12] or null
+  // time segmentation (few runs, long series): blockIdx.x = run * nseg + seg, samples
+  // [seg*seg_len, min(n, (seg+1)*seg_len)).  pass 0: write outputs, GM state at the segment
+  // start taken from seg_carry[run][seg][6] (all zero for seg 0); pass 1: no output, only the
+  // zero-state GM response at the segment end -> seg_end[run][seg][6]
+  int64_t seg_len;
+  int nseg;
+  int pass;
+  double* seg_carry;
+  double* seg_end;
 };
 
 // inclusive scan of y_i = a y_{i-1} + x_i over the block (zero initial state).
@@ -51,7 +60,10 @@ __device__ __forceinline__ double gm_block_scan(double x, const double* apow, do
 __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
   __shared__ double apow[6][kNoiseThreads + 1];
   __shared__ double sh_w[kNoiseWarps];
-  const int64_t run = blockIdx.x;
+  const int64_t run = blockIdx.x / p.nseg;
+  const int seg = static_cast<int>(blockIdx.x % p.nseg);
+  const int64_t seg_lo = seg * p.seg_len;
+  const int64_t seg_hi = min64(p.n, seg_lo + p.seg_len);
   const int64_t grun = p.run_offset + run;
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
   const int i = threadIdx.x;
@@ -69,11 +81,15 @@ __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_c
       phase[c] = (uniform01(0xFFFFFFFFu, kDrawPhase + c, run_lo, run_hi, p.k0, p.k1) * 2.0) * kPi;
   }
   double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // d at the first sample of the tile
+  if (p.pass == 0 && p.seg_carry) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) carry[c] = p.seg_carry[(run * p.nseg + seg) * 6 + c];
+  }
   __syncthreads();
 
-  for (int64_t tile0 = 0; tile0 < p.n; tile0 += kNoiseThreads) {
+  for (int64_t tile0 = seg_lo; tile0 < seg_hi; tile0 += kNoiseThreads) {
     const int64_t t = tile0 + i;
-    const bool live = t < p.n;
+    const bool live = t < seg_hi;
     double m[6], z[6];
     if (live) {
       noisy_sample(p, p.ref_accel + t * 3, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo,
@@ -106,7 +122,7 @@ __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_c
       carry[c] = apow[c][kNoiseThreads] * carry[c] + total;
       __syncthreads();
     }
-    if (live) {
+    if (live && p.pass == 0) {
       const int64_t o = run * p.osr + t * p.ost;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -128,6 +144,27 @@ __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_c
         }
       }
     }
+  }
+  if (p.pass == 1 && threadIdx.x == 0) {
+    // the tiles of a segment are whole (seg_len is a multiple of the tile) except in the last
+    // segment, whose end value is never used
+#pragma unroll
+    for (int c = 0; c < 6; ++c) p.seg_end[(run * p.nseg + seg) * 6 + c] = carry[c];
+  }
+}
+
+// carry-in of every segment from the zero-state segment responses: c[s+1] = a^L c[s] + E[s]
+__global__ void noise_carry_kernel(NoiseParams p) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= p.runs * 6) return;
+  const int64_t run = idx / 6;
+  const int c = static_cast<int>(idx % 6);
+  const double a = (c < 3) ? p.accel.gm_a[c] : p.gyro.gm_a[c - 3];
+  const double aL = pow(a, static_cast<double>(p.seg_len));
+  double cin = 0.0;
+  for (int s = 0; s < p.nseg; ++s) {
+    p.seg_carry[(run * p.nseg + s) * 6 + c] = cin;
+    cin = aL * cin + p.seg_end[(run * p.nseg + s) * 6 + c];
   }
 }
 

@@ -194,3 +194,15 @@ def test_config3_true_long_drive_through_sim(eng):
     assert_close(err[:, 5], o_err[:, 5], 1e-6, 1.0, 'alt')
     st = sim.get_error_stats('pos', -1, extra_opt='ned')
     assert st['units'] == "['m', 'm', 'm']" and np.isfinite(st['std']).all()
+
+
+def test_k1_time_segmented_path(eng):
+    """Few runs + long series: K1 splits the time axis into segments (two-pass Gauss-Markov
+    carry).  Same numbers as the serial oracle, including across segment boundaries."""
+    n, fs, R = 700001, 100.0, 2
+    gyro, accel, ini, _ = synthetic_drive(n, fs)
+    fast_g = dict(LOW_G, b_corr=np.array([0.5, 100.0, np.inf]))     # fast, slow and white drift
+    g, a = eng.imu_noise(fs, R, eng.to_device(gyro), eng.to_device(accel), fast_g, LOW_A, 3, 40)
+    og, oa = oracle_c.imu_noise(fs, gyro, accel, fast_g, LOW_A, 3, np.arange(40, 40 + R))
+    assert_close(g.cpu().numpy(), og, 1e-11, 1.0, 'gyro')
+    assert_close(a.cpu().numpy(), oa, 1e-11, 1.0, 'accel')
