@@ -13,7 +13,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(CSRC, 'libb2ins.so')
+# B2INS_LIB lets tools load an experimental build (tools/variants.sh); the product uses the default
+LIB = os.environ.get('B2INS_LIB') or os.path.join(CSRC, 'libb2ins.so')
 SOURCES = ['b2ins_api.cu']
 DEPS = ['b2ins_api.cu', 'common.cuh', 'fastmath64.cuh', 'mech.cuh', 'mc_kernel.cuh', 'noise_kernel.cuh',
         'stats_kernel.cuh', 'allan_kernel.cuh', 'psd_kernel.cuh', 'pathgen_host.h', os.path.join('..', '..', 'include', 'b2ins.h')]
@@ -29,6 +30,8 @@ def find_nvcc():
 
 
 def stale():
+    if os.environ.get('B2INS_LIB'):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

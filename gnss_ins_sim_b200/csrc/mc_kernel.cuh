@@ -256,9 +256,12 @@ __device__ __forceinline__ double ipow(double a, int e) {
 // resident CTAs per SM the register allocation must allow: the throughput configuration
 // (G = 1) wants many warps per scheduler to cover FP64 latency; wide groups are latency bound
 // by the serial recurrence and keep their registers
+#ifndef B2INS_G1_MINBLOCKS
+#define B2INS_G1_MINBLOCKS 4   // measured best of 3/4/5 (tools/variants.sh, profiles/)
+#endif
 template <int G>
 struct MinBlocks {
-  static constexpr int value = (G == 1) ? 4 : (G == 2 ? 3 : 2);
+  static constexpr int value = (G == 1) ? B2INS_G1_MINBLOCKS : (G == 2 ? 3 : 2);
 };
 
 template <int G, int RF, bool FED, bool PROC>

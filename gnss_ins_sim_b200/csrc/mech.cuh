@@ -53,10 +53,6 @@ __device__ __forceinline__ Dcm dcm_from_sincos(const SinCos3& t) {
   return c;
 }
 
-__device__ __forceinline__ Vec3 mul(const Dcm& c, const Vec3& v) {  // c . v
-  return Vec3{c.c00 * v.x + c.c01 * v.y + c.c02 * v.z, c.c10 * v.x + c.c11 * v.y + c.c12 * v.z,
-              c.c20 * v.x + c.c21 * v.y + c.c22 * v.z};
-}
 __device__ __forceinline__ Vec3 mul_t(const Dcm& c, const Vec3& v) {  // c^T . v
   return Vec3{c.c00 * v.x + c.c10 * v.y + c.c20 * v.z, c.c01 * v.x + c.c11 * v.y + c.c21 * v.z,
               c.c02 * v.x + c.c12 * v.y + c.c22 * v.z};
