@@ -169,7 +169,7 @@ def run_reference(args):
     })
 
 
-def cpu_baseline_sample(g, nav, imu, budget_s=10.0):
+def cpu_baseline_sample(g, nav, imu, budget_s=4.0):
     """Rank 0, N = 1: the C port timed on the host cores on a bounded sample of the workload."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle_c

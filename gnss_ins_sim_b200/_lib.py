@@ -64,6 +64,8 @@ SIGNATURES = {
     'b2ins_mc_plan_create': (_I, [_L, _L, _I, _I, ctypes.POINTER(ctypes.c_void_p)]),
     'b2ins_mc_plan_run': (_I, [_P, _MC, _P, _P, _P, _P, _P, _P]),
     'b2ins_mc_plan_destroy': (_I, [_P]),
+    'b2ins_mc_plan_err_device': (_P, [_P]),
+    'b2ins_mc_plan_stream': (_P, [_P]),
     'b2ins_error_stats_workspace_bytes': (_L, [_I]),
     'b2ins_error_partial_f64': (_I, [_L, _I, _P, _P, _P, _P]),
     'b2ins_error_partial2_f64': (_I, [_L, _I, _P, _P, _P, _P, _P]),

@@ -602,7 +602,7 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const dou
             "cfg does not fit the plan (n=%lld runs<=%lld ini=[%d][%d])",
             static_cast<long long>(plan->n), static_cast<long long>(plan->max_runs), plan->ini_sets,
             plan->ini_rows);
-  ARG_CHECK(ref_gyro && ref_accel && ref_nav_end && ini && stats, "null buffer");
+  ARG_CHECK(ref_gyro && ref_accel && ref_nav_end && ini, "null buffer");
   ARG_CHECK(cfg->stats_start < 0 && cfg->dump_runs == 0,
             "a plan computes end-point errors and their statistics only");
   const int64_t n = plan->n;
@@ -631,16 +631,21 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const dou
                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                          plan->stream);
   if (rc != B2INS_OK) return rc;
-  rc = b2ins_error_stats_f64(cfg->runs, 9, d_err, d_stats, plan->d_ws, plan->stream);
-  if (rc != B2INS_OK) return rc;
+  if (stats) {
+    rc = b2ins_error_stats_f64(cfg->runs, 9, d_err, d_stats, plan->d_ws, plan->stream);
+    if (rc != B2INS_OK) return rc;
+  }
   const size_t out_d = 27 + (end_err ? static_cast<size_t>(cfg->runs) * 9 : 0);
   CU_CHECK(cudaMemcpyAsync(plan->h_out, plan->d_out, out_d * sizeof(double), cudaMemcpyDeviceToHost,
                            plan->stream));
   CU_CHECK(cudaStreamSynchronize(plan->stream));
-  std::memcpy(stats, plan->h_out, 27 * sizeof(double));
+  if (stats) std::memcpy(stats, plan->h_out, 27 * sizeof(double));
   if (end_err) std::memcpy(end_err, plan->h_out + 27, static_cast<size_t>(cfg->runs) * 9 * sizeof(double));
   return B2INS_OK;
 }
+
+double* b2ins_mc_plan_err_device(b2ins_mc_plan* plan) { return plan ? plan->d_out + 27 : nullptr; }
+void* b2ins_mc_plan_stream(b2ins_mc_plan* plan) { return plan ? plan->stream : nullptr; }
 
 // ---------------------------------------------------------------- K3 --------
 int64_t b2ins_error_stats_workspace_bytes(int ncomp) {

@@ -95,6 +95,19 @@ def merge_stats(blocks):
 
 
 _mergers = {}
+_p2p = {}
+
+
+def fused_exchange(ncomp=9):
+    """A cached P2PStats for the WORLD group, or None if symmetric memory is unavailable (every
+    rank must call this the same number of times: construction is collective)."""
+    key = (ncomp, world())
+    if key not in _p2p:
+        try:
+            _p2p[key] = P2PStats(ncomp) if initialised() and td.get_backend() == 'nccl' else None
+        except Exception:
+            _p2p[key] = None
+    return _p2p[key]
 
 
 def combine_local_stats(stats, local_runs):
@@ -169,14 +182,20 @@ class P2PStats:
         torch.cuda.synchronize()
         td.barrier()                      # every window is zeroed before anyone's first store
 
-    def __call__(self, end_err, local_runs):
-        """end_err: CUDA f64 [local_runs, nc] (ignored if local_runs == 0) -> CUDA [3, nc]."""
+    def __call__(self, end_err, local_runs, stream_ptr=None):
+        """end_err: CUDA f64 [local_runs, nc] tensor or a raw device address (ignored if
+        local_runs == 0); stream_ptr: raw cudaStream_t (default: torch's current stream)
+        -> CUDA [3, nc]."""
         import ctypes
         self.seq += 1
-        err = end_err if local_runs else self.empty
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if not local_runs:
+            ptr = self.empty.data_ptr()
+        else:
+            ptr = end_err.data_ptr() if isinstance(end_err, torch.Tensor) else int(end_err)
+        stream = ctypes.c_void_p(stream_ptr if stream_ptr is not None
+                                 else torch.cuda.current_stream().cuda_stream)
         self._check(self._lib.b2ins_error_stats_exchange_f64(
-            int(local_runs), self.nc, ctypes.c_void_p(err.data_ptr()), self.r, self.w, self.ptrs,
+            int(local_runs), self.nc, ctypes.c_void_p(ptr), self.r, self.w, self.ptrs,
             self.seq, ctypes.c_void_p(self.out.data_ptr()), ctypes.c_void_p(self.flag.data_ptr()),
             stream))
         return self.out

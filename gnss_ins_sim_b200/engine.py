@@ -211,15 +211,22 @@ class McPlan:
         _lib.check(self._lib.b2ins_mc_plan_create(self.n, self.max_runs, self.ini_sets,
                                                   self.ini_rows, ctypes.byref(self._h)))
 
-    def run(self, cfg, ref_gyro, ref_accel, ref_nav_end, ini, want_err=True):
+    def run(self, cfg, ref_gyro, ref_accel, ref_nav_end, ini, want_err=True, want_stats=True):
         """Host float64 C-contiguous arrays in (ref_nav_end: the 9 values att,pos,vel of the true
-        trajectory at its last sample); (end_err [runs,9] or None, stats [3,9]) out."""
+        trajectory at its last sample); (end_err [runs,9] or None, stats [3,9] or None) out."""
         hp = _lib.host_ptr
-        stats = np.empty((3, 9))
+        stats = np.empty((3, 9)) if want_stats else None
         err = np.empty((cfg.runs, 9)) if want_err else None
         _lib.check(self._lib.b2ins_mc_plan_run(self._h, ctypes.byref(cfg), hp(ref_gyro), hp(ref_accel),
                                                hp(ref_nav_end), hp(ini), hp(err), hp(stats)))
         return err, stats
+
+    def err_device_ptr(self):
+        """Device address of the plan's end_err buffer (multi-GPU statistics exchange)."""
+        return self._lib.b2ins_mc_plan_err_device(self._h)
+
+    def stream_ptr(self):
+        return self._lib.b2ins_mc_plan_stream(self._h)
 
     def close(self):
         if self._h:

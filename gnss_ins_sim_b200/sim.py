@@ -437,13 +437,22 @@ class Sim(object):
             # the plan path on this rank's shard (pinned staging, one H2D, K12, K3, one D2H);
             # with several ranks the [3][9] shard statistics are merged by one all_gather
             err, stats = np.zeros((0, 9)), np.zeros((3, 9))
+            p2p = dist.fused_exchange(9) if dist.world() > 1 and (hi - lo) * 9 <= (1 << 17) else None
+            plan = None
             if hi > lo:
                 cfg = self._mc_config(i, hi - lo, lo)
                 t = self._traj
                 plan = engine.get_plan(cfg.n, cfg.runs, cfg.ini_sets, cfg.ini_rows)
-                err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav_end, algo.ini_sets)
+                err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav_end, algo.ini_sets,
+                                      want_stats=p2p is None)
             self._mc[i]['end_err'] = err
-            self.err_stats[name] = dist.combine_local_stats(stats, hi - lo)
+            if p2p is not None:
+                # K3x on the plan's device buffer: statistics + NVLink exchange + merge, one kernel
+                # (plan.run has synchronised: the errors are final; torch's stream orders the copy)
+                merged = p2p(plan.err_device_ptr() if plan else None, hi - lo)
+                self.err_stats[name] = merged.cpu().numpy().copy()
+            else:
+                self.err_stats[name] = dist.combine_local_stats(stats, hi - lo)
         else:
             d = self._dev
             err, stats = np.zeros((0, 9)), np.zeros((3, 9))

@@ -189,8 +189,8 @@ int b2ins_mc_free_integration_f64_host(const b2ins_mc_config* cfg,
  * b2ins_mc_free_integration_f64_host without the per-call allocations: stage the host
  * inputs into pinned memory, H2D copy (true IMU samples, ref_nav_end = the 9 values
  * att,pos,vel of the true trajectory at sample n-1, ini),
- * K12, K3, ONE D2H copy (stats [3][9] and, if end_err != NULL, the [runs][9] end-point
- * errors), synchronise.  This is what Sim.run() calls on a single GPU.  A plan is bound to
+ * K12, K3, ONE D2H copy (stats [3][9] -- skipped with K3 if stats == NULL -- and, if end_err !=
+ * NULL, the [runs][9] end-point errors), synchronise.  This is what Sim.run() calls on a single GPU.  A plan is bound to
  * the device current at creation and is not thread-safe (one plan per thread). */
 typedef struct b2ins_mc_plan b2ins_mc_plan;
 int b2ins_mc_plan_create(int64_t n, int64_t max_runs, int ini_sets, int ini_rows,
@@ -199,6 +199,11 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg,
                       const double* ref_gyro, const double* ref_accel, const double* ref_nav_end,
                       const double* ini, double* end_err, double* stats);
 int b2ins_mc_plan_destroy(b2ins_mc_plan* plan);
+/* Multi-GPU use: plan_run with stats == NULL skips K3 and only synchronises the end-point errors;
+ * the DEVICE address of the plan's [max_runs][9] end_err buffer (valid until the next plan_run)
+ * can then be handed to b2ins_error_stats_exchange_f64 on plan_stream(). */
+double* b2ins_mc_plan_err_device(b2ins_mc_plan* plan);
+void* b2ins_mc_plan_stream(b2ins_mc_plan* plan);
 
 /* ---- K3: ensemble error statistics ---------------------------------------
  * Replaces InsDataMgr.__end_point_error_stats / __array_stats
