@@ -27,17 +27,22 @@ class Allan(object):
                                          np.asarray(set_of_input[2])[None])
         self.results = [tau, ad_a[0], ad_g[0]]
 
-    def run_batch(self, fs, accel, gyro, to_host=True):
+    def run_batch(self, fs, accel, gyro, to_host=True, channel_major=False):
         '''
-        accel, gyro: [R, n, 3].  Returns tau [ntau], ad_accel [R, ntau, 3], ad_gyro [R, ntau, 3]
+        accel, gyro: [R, n, 3] (the reference's per-run arrays) or, channel_major, [R, 3, n].
+        Returns tau [ntau], ad_accel [R, ntau, 3], ad_gyro [R, ntau, 3]
         (Allan DEVIATION = sqrt(avar), allan_analysis.py:47-49).
         '''
         a = engine.to_device(accel)
         g = engine.to_device(gyro)
-        R, n, _ = a.shape
         out = []
-        for x in (a, g):          # each [R, n, 3]: 3R interleaved series, read in place (no copy)
-            avar, tau = engine.allan(fs, x, n, R * 3, inner=3, outer_stride=3 * n, sample_stride=3)
+        for x in (a, g):
+            if channel_major:     # 3R contiguous series: the bulk-copy front end of K4
+                R, _, n = x.shape
+                avar, tau = engine.allan(fs, x, n, R * 3)
+            else:                 # 3R interleaved series, read in place (no copy)
+                R, n, _ = x.shape
+                avar, tau = engine.allan(fs, x, n, R * 3, inner=3, outer_stride=3 * n, sample_stride=3)
             out.append(torch.sqrt(avar).reshape(R, 3, -1).permute(0, 2, 1).contiguous())
         if to_host:
             return tau.cpu().numpy(), out[0].cpu().numpy(), out[1].cpu().numpy()

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.environ.get('B2INS_LIB') or os.path.join(CSRC, 'libb2ins.so')
 SOURCES = ['b2ins_api.cu']
 DEPS = ['b2ins_api.cu', 'common.cuh', 'fastmath64.cuh', 'mech.cuh', 'mc_kernel.cuh', 'noise_kernel.cuh',
-        'stats_kernel.cuh', 'allan_kernel.cuh', 'psd_kernel.cuh', 'pathgen_host.h', os.path.join('..', '..', 'include', 'b2ins.h')]
+        'stats_kernel.cuh', 'allan_kernel.cuh', 'psd_kernel.cuh', 'gps_kernel.cuh', 'pathgen_host.h', os.path.join('..', '..', 'include', 'b2ins.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 

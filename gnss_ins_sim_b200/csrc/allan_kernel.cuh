@@ -37,10 +37,12 @@ struct AllanLevelParams {
   int jmax;              // cluster multipliers 1..jmax are wanted at this level
   int64_t chunk_first;   // this launch covers chunks [chunk_first, chunk_first + chunk_count)
   int64_t chunk_count;
+  int64_t src_pitch;     // row pitch of S_k (levels >= 1) and of S_{k+1}: even, so that rows are
+  int64_t next_pitch;    // 16-byte aligned for the bulk copies
 };
 
 __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid_constant__ AllanLevelParams p) {
-  extern __shared__ double tile[];  // [kAllanHalo + kAllanChunk + 1] prefix, tile[0] = 0
+  extern __shared__ __align__(128) double tile[];  // [kAllanHalo + kAllanChunk + 1] prefix, tile[0] = 0
   __shared__ double red[kAllanThreads / 32][9];
   __shared__ double sh_scan[kAllanThreads];
   const int64_t series = blockIdx.x / p.chunk_count;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
     base = p.src + (series / p.inner) * p.outer_stride + (series % p.inner);
     stride = p.sample_stride;
   } else {
-    base = p.src + series * p.len;
+    base = p.src + series * p.src_pitch;
     stride = 1;
   }
   const double off = base[lo * stride];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
       const int64_t di = d_lo + i;
       if (di < p.next_len) {
         const int e = halo + i * 10;
-        p.next[series * p.next_len + di] = (tile[e + 10] - tile[e]) + 10.0 * off;
+        p.next[series * p.next_pitch + di] = (tile[e + 10] - tile[e]) + 10.0 * off;
       }
     }
   }
@@ -141,161 +143,357 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
 
 // ---- fast path: FULL chunks ---------------------------------------------------------------
 // A full chunk holds an integer number of clusters of every size (5040 = 2 lcm(1..10)), so the
-// cluster sums can be built hierarchically in registers, a few samples per work item, without
-// any bound checks:
-//   role A (8 samples / item, from a copy padded 8 -> 9 doubles: conflict-free):  j = 1, 2, 4, 8
-//   role B (18 samples / item):  j = 3, 6, 9        role C (10 / item):  j = 5 and the decade sums
-//   role D (7 / item):  j = 7
-// An item also rebuilds the LAST clusters of the samples just before it (at most 9 samples, the
-// halo for item 0) for the difference that straddles its left edge.  ~25 instructions per sample
-// against ~107 of the prefix-sum kernel above, which remains the path for the ragged last chunk.
-constexpr int kAllanPad8 = kAllanChunk / 8 * 9;
-constexpr int kAllanFullThreads = 512;   // two 86 KB CTAs per SM: 32 warps to hide the load latency
+// cluster sums are built hierarchically IN REGISTERS, without bound checks, by four kinds of work
+// items (23 warps):
+//   A1 (105 items of 48 samples, 4 warps): j = 2, 4, 8   (pairs, pairs of pairs, ...)
+//   A2 (280 items of 18 samples, 9 warps): j = 3, 6, 9   (triples, pairs / triples of triples)
+//   C1 (120 items of 42 samples, 4 warps): j = 1, 7
+//   C2 (168 items of 30 samples, 6 warps): j = 5 and the decade sums that feed the next level
+// (~9 FP64 instructions per sample in all).  An item is read with 128-bit shared-memory loads;
+// they are conflict-free when the item pitch is an odd number of 16-byte units: 9, 21 and 15 for
+// A2, C1 and C2 on the raw tile, while A1 (24 units) reads a copy padded 48 -> 50 doubles.  The
+// difference that straddles the left edge of an item uses the neighbour's last cluster sums,
+// exchanged through shared memory (the halo for item 0).  Two front ends fill the two copies:
+//   allan_stream_kernel  contiguous, 16-byte aligned series: persistent CTA per SM, the raw tile
+//                        arrives by one TMA bulk copy per tile, two tiles in flight (mbarriers);
+//   allan_full_kernel    any stride / alignment: per-thread loads, one tile per CTA.
+// The prefix-sum kernel above remains the path for the ragged last chunk of a series.
+constexpr int kAllanItemsA1 = kAllanChunk / 48;   // 105
+constexpr int kAllanItemsA2 = kAllanChunk / 18;   // 280
+constexpr int kAllanItemsC1 = kAllanChunk / 42;   // 120
+constexpr int kAllanItemsC2 = kAllanChunk / 30;   // 168
+constexpr int kAllanPad48 = kAllanItemsA1 * 50;   // 5250
+constexpr int kAllanWarpsA1 = 4, kAllanWarpsA2 = 9, kAllanWarpsC1 = 4, kAllanWarpsC2 = 6;
+constexpr int kAllanFastWarps = kAllanWarpsA1 + kAllanWarpsA2 + kAllanWarpsC1 + kAllanWarpsC2;   // 23
+constexpr int kAllanFastThreads = 32 * kAllanFastWarps;   // 736
+constexpr int kAllanLead = kAllanHalo + 1;        // 10: chunk element e lives at raw[10 + e]
+constexpr int kAllanRawLen = 5056;                // >= 10 + 5040, a multiple of 2
+
+struct AllanTileSmem {
+  double last_a1[kAllanItemsA1][3];
+  double last_a2[kAllanItemsA2][3];
+  double last_c1[kAllanItemsC1];
+  double last_c2[kAllanItemsC2];
+  double red[kAllanFastWarps][4];
+};
 
 __device__ __forceinline__ double sq_acc(double a, double b, double acc) {
   const double d = a - b;
   return fma(d, d, acc);
 }
 
-__global__ void __launch_bounds__(kAllanFullThreads) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
-  extern __shared__ double smem[];
-  double* raw = smem;                                // [kAllanHalo + kAllanChunk]: raw[h + e]
-  double* pad8 = smem + kAllanHalo + kAllanChunk + 1;  // [kAllanPad8]: element e at e + e/8
-  __shared__ double red[kAllanFullThreads / 32][9];
+// sum over i = 1..N-1 of (c[i] - c[i-1])^2 in interleaved accumulators (the serial FMA chain of a
+// single accumulator would cost 8 cycles per link)
+template <int N>
+__device__ __forceinline__ double sum_sq_diff(const double (&c)[N]) {
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 1; i < N; ++i) a[i & 3] = sq_acc(c[i], c[i - 1], a[i & 3]);
+  return (a[0] + a[1]) + (a[2] + a[3]);
+}
+
+// Warp totals of four values per lane in 5 packed butterfly steps; lane L returns the total of
+// value number L >> 3.  Fixed pairing: deterministic.
+__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, int lane) {
+  const bool up16 = lane & 16;
+  const double w0 = (up16 ? v2 : v0) + __shfl_xor_sync(0xffffffffu, up16 ? v0 : v2, 16);
+  const double w1 = (up16 ? v3 : v1) + __shfl_xor_sync(0xffffffffu, up16 ? v1 : v3, 16);
+  const bool up8 = lane & 8;
+  double t = (up8 ? w1 : w0) + __shfl_xor_sync(0xffffffffu, up8 ? w0 : w1, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
+}
+
+// One tile, both copies in shared memory (offset-subtracted): x[e], e in [-9, 5040), and pad
+// (element e at e + 2 (e / 48)).  Called by every thread of the CTA; contains two __syncthreads.
+__device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, int64_t series, int64_t chunk,
+                                                   const double* x, const double* pad, double off10,
+                                                   AllanTileSmem& sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kW1 = kAllanWarpsA1, kW2 = kW1 + kAllanWarpsA2, kW3 = kW2 + kAllanWarpsC1;
+  const int role = (warp >= kW1) + (warp >= kW2) + (warp >= kW3);
+  const int item = tid - 32 * (role == 0 ? 0 : role == 1 ? kW1 : role == 2 ? kW2 : kW3);
+  const bool has_prev = chunk != 0;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;   // the role's sums of squared differences
+  double f0 = 0.0, f1 = 0.0, f2 = 0.0;   // first clusters of the item
+  if (role == 0) {
+    if (item < kAllanItemsA1) {   // j = 2, 4, 8 in two blocks of 24 samples
+      const double2* src = reinterpret_cast<const double2*>(pad + 50 * item);
+      double pP = 0.0, pQ = 0.0, pO = 0.0;
+#pragma unroll
+      for (int sb = 0; sb < 2; ++sb) {
+        double P[12], Q[6], O[3];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const double2 t = src[12 * sb + i];
+          P[i] = t.x + t.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Q[i] = P[2 * i] + P[2 * i + 1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) O[i] = Q[2 * i] + Q[2 * i + 1];
+        if (sb == 0) {
+          f0 = P[0]; f1 = Q[0]; f2 = O[0];
+        } else {
+          v0 = sq_acc(P[0], pP, v0); v1 = sq_acc(Q[0], pQ, v1); v2 = sq_acc(O[0], pO, v2);
+        }
+        v0 += sum_sq_diff(P); v1 += sum_sq_diff(Q); v2 += sum_sq_diff(O);
+        pP = P[11]; pQ = Q[5]; pO = O[2];
+      }
+      sm.last_a1[item][0] = pP; sm.last_a1[item][1] = pQ; sm.last_a1[item][2] = pO;
+    }
+  } else if (role == 1) {
+    if (item < kAllanItemsA2) {   // j = 3, 6, 9 on 18 samples
+      const double2* src = reinterpret_cast<const double2*>(x + 18 * item);
+      double y[18], T[6], S[3], N[2];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const double2 t = src[i];
+        y[2 * i] = t.x;
+        y[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) T[i] = (y[3 * i] + y[3 * i + 1]) + y[3 * i + 2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) S[i] = T[2 * i] + T[2 * i + 1];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) N[i] = (T[3 * i] + T[3 * i + 1]) + T[3 * i + 2];
+      f0 = T[0]; f1 = S[0]; f2 = N[0];
+      v0 = sum_sq_diff(T); v1 = sum_sq_diff(S); v2 = sum_sq_diff(N);
+      sm.last_a2[item][0] = T[5]; sm.last_a2[item][1] = S[2]; sm.last_a2[item][2] = N[1];
+    }
+  } else if (role == 2) {
+    if (item < kAllanItemsC1) {   // j = 1, 7 in three blocks of 14 samples
+      const double2* src = reinterpret_cast<const double2*>(x + 42 * item);
+      double py = 0.0, pG = 0.0;
+      // j = 1: the left neighbour of the item's first sample is in the raw tile (halo for item 0)
+      const bool left = item > 0 || has_prev;
+      if (left) py = x[42 * item - 1];
+#pragma unroll
+      for (int sb = 0; sb < 3; ++sb) {
+        double y[14], G[2];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const double2 t = src[7 * sb + i];
+          y[2 * i] = t.x;
+          y[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          G[i] = ((y[7 * i] + y[7 * i + 1]) + (y[7 * i + 2] + y[7 * i + 3])) + ((y[7 * i + 4] + y[7 * i + 5]) + y[7 * i + 6]);
+        if (sb == 0) {
+          f1 = G[0];
+          if (left) v0 = sq_acc(y[0], py, v0);
+        } else {
+          v0 = sq_acc(y[0], py, v0);
+          v1 = sq_acc(G[0], pG, v1);
+        }
+        v0 += sum_sq_diff(y);
+        v1 = sq_acc(G[1], G[0], v1);
+        py = y[13]; pG = G[1];
+      }
+      sm.last_c1[item] = pG;
+    }
+  } else {
+    if (item < kAllanItemsC2) {   // j = 5 and the decade sums, in three blocks of 10 samples
+      const double2* src = reinterpret_cast<const double2*>(x + 30 * item);
+      double* nx = p.next + series * p.next_pitch + (chunk * kAllanChunk) / 10 + 3 * item;
+      double pF = 0.0;
+#pragma unroll
+      for (int sb = 0; sb < 3; ++sb) {
+        double y[10];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const double2 t = src[5 * sb + i];
+          y[2 * i] = t.x;
+          y[2 * i + 1] = t.y;
+        }
+        const double F0 = ((y[0] + y[1]) + (y[2] + y[3])) + y[4];
+        const double F1 = ((y[5] + y[6]) + (y[7] + y[8])) + y[9];
+        if (sb == 0) f0 = F0; else v0 = sq_acc(F0, pF, v0);
+        v0 = sq_acc(F1, F0, v0);
+        pF = F1;
+        if (p.next_len > 0) nx[sb] = (F0 + F1) + off10;
+      }
+      sm.last_c2[item] = pF;
+    }
+  }
+  __syncthreads();
+  // the difference across the left edge of every item: neighbour's last clusters, halo for item 0
+  if (role == 0) {
+    if (item > 0 && item < kAllanItemsA1) {
+      const double* l = sm.last_a1[item - 1];
+      v0 = sq_acc(f0, l[0], v0); v1 = sq_acc(f1, l[1], v1); v2 = sq_acc(f2, l[2], v2);
+    } else if (item == 0 && has_prev) {
+      const double pp3 = x[-2] + x[-1], pp2 = x[-4] + x[-3], pp1 = x[-6] + x[-5], pp0 = x[-8] + x[-7];
+      v0 = sq_acc(f0, pp3, v0);
+      v1 = sq_acc(f1, pp2 + pp3, v1);
+      v2 = sq_acc(f2, (pp0 + pp1) + (pp2 + pp3), v2);
+    }
+  } else if (role == 1) {
+    if (item > 0 && item < kAllanItemsA2) {
+      const double* l = sm.last_a2[item - 1];
+      v0 = sq_acc(f0, l[0], v0); v1 = sq_acc(f1, l[1], v1); v2 = sq_acc(f2, l[2], v2);
+    } else if (item == 0 && has_prev) {
+      const double u2 = (x[-3] + x[-2]) + x[-1], u1 = (x[-6] + x[-5]) + x[-4], u0 = (x[-9] + x[-8]) + x[-7];
+      v0 = sq_acc(f0, u2, v0);
+      v1 = sq_acc(f1, u1 + u2, v1);
+      v2 = sq_acc(f2, (u0 + u1) + u2, v2);
+    }
+  } else if (role == 2) {
+    if (item > 0 && item < kAllanItemsC1) {
+      v1 = sq_acc(f1, sm.last_c1[item - 1], v1);
+    } else if (item == 0 && has_prev) {
+      v1 = sq_acc(f1, ((x[-7] + x[-6]) + (x[-5] + x[-4])) + ((x[-3] + x[-2]) + x[-1]), v1);
+    }
+  } else {
+    if (item > 0 && item < kAllanItemsC2) {
+      v0 = sq_acc(f0, sm.last_c2[item - 1], v0);
+    } else if (item == 0 && has_prev) {
+      v0 = sq_acc(f0, ((x[-5] + x[-4]) + (x[-3] + x[-2])) + x[-1], v0);
+    }
+  }
+  // ---- block reduction: one packed butterfly per warp, then the role's warps in order ------------
+  const double t = warp_sum4(v0, v1, v2, 0.0, lane);
+  if ((lane & 7) == 0) sm.red[warp][lane >> 3] = t;
+  __syncthreads();
+  if (tid < 9) {
+    // j = tid + 1 is held by role {2,0,1,0,3,1,2,0,1}[tid] in column {0,0,0,1,0,1,1,2,2}[tid]
+    const int r = static_cast<int>((0x102130102ull >> (4 * tid)) & 15);
+    const int c = static_cast<int>((0x221101000ull >> (4 * tid)) & 15);
+    const int w0 = r == 0 ? 0 : r == 1 ? kW1 : r == 2 ? kW2 : kW3;
+    const int w1 = r == 0 ? kW1 : r == 1 ? kW2 : r == 2 ? kW3 : kAllanFastWarps;
+    double v = 0.0;
+    for (int w = w0; w < w1; ++w) v += sm.red[w][c];
+    p.partial[(series * p.chunks + chunk) * 9 + tid] = (tid < p.jmax) ? v : 0.0;
+  }
+}
+
+template <bool UNIT>   // UNIT: consecutive samples are adjacent in memory
+__global__ void __launch_bounds__(kAllanFastThreads, 1) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
+  extern __shared__ __align__(128) double smem[];
+  double* raw = smem;                                  // [kAllanRawLen]
+  double* pad48 = smem + kAllanRawLen;                 // [kAllanPad48]: element e at e + 2*(e/48)
+  __shared__ AllanTileSmem sm;
+  __shared__ double sh_off10;
   const int64_t series = blockIdx.x / p.chunk_count;
   const int64_t chunk = p.chunk_first + blockIdx.x % p.chunk_count;
   const int64_t c0 = chunk * kAllanChunk;
-  const int h = (chunk == 0) ? 0 : kAllanHalo;
   const bool has_prev = chunk != 0;
-  const int64_t lo = c0 - h;
+  const int tid = threadIdx.x;
   const double* base;
   int64_t stride;
   if (p.level0) {
     base = p.src + (series / p.inner) * p.outer_stride + (series % p.inner);
-    stride = p.sample_stride;
+    stride = UNIT ? 1 : p.sample_stride;
   } else {
-    base = p.src + series * p.len;
+    base = p.src + series * p.src_pitch;
     stride = 1;
   }
-  const double off = base[lo * stride];
+  double* x = raw + kAllanLead;                        // x[e], e in [-9, kAllanChunk); 16-B aligned
   {
-    // all the loads of a thread are issued before the first use: 20 independent requests in flight
-    // per thread instead of a load -> store chain that exposes the DRAM latency 20 times
-    constexpr int kPer = (kAllanChunk + kAllanHalo + kAllanFullThreads - 1) / kAllanFullThreads;
-    double v[kPer];
+    // loaders: thread (g, pos) loads element 48 (15 q + g) + pos in pass q; every load is issued
+    // before the first use (7 independent requests in flight per thread)
+    constexpr int kLoaders = 720;   // 15 blocks of 48 per pass, 7 passes
+    const int g = tid / 48, pos = tid - 48 * g;
+    const double* src = base + (c0 + 48 * g + pos) * stride;
+    const double off = base[(c0 - (has_prev ? kAllanHalo : 0)) * stride];
+    double v[7];
+    double hv = 0.0;
+    if (tid < kLoaders) {
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int i = threadIdx.x + q * kAllanFullThreads;
-      v[q] = (i < kAllanChunk + h) ? base[(lo + i) * stride] : 0.0;
+      for (int q = 0; q < 7; ++q) v[q] = src[static_cast<int64_t>(q) * kLoaders * stride];
+    } else if (has_prev && tid < kLoaders + kAllanHalo) {
+      hv = base[(c0 - kAllanHalo + (tid - kLoaders)) * stride];
     }
+    if (tid < kLoaders) {
+      double* xr = x + 48 * g + pos;
+      double* xp = pad48 + 50 * g + pos;
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int i = threadIdx.x + q * kAllanFullThreads;
-      if (i < kAllanChunk + h) {
+      for (int q = 0; q < 7; ++q) {
         const double w = v[q] - off;
-        raw[i] = w;
-        const int e = i - h;
-        if (e >= 0) pad8[e + (e >> 3)] = w;
+        xr[q * kLoaders] = w;
+        xp[q * 15 * 50] = w;
       }
+    } else if (has_prev && tid < kLoaders + kAllanHalo) {
+      x[tid - kLoaders - kAllanHalo] = hv - off;
     }
+    if (tid == 0) sh_off10 = 10.0 * off;   // decade sums carry the offset back
   }
   __syncthreads();
-  const double* x = raw + h;   // x[e], e in [-h, kAllanChunk)
-  double a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0;
-  const int jm = p.jmax;
+  allan_tile_compute(p, series, chunk, x, pad48, sh_off10, sm);
+}
 
-  // ---- role A: j = 1, 2, 4, 8 ------------------------------------------------------------
-  for (int it = threadIdx.x; it < kAllanChunk / 8; it += kAllanFullThreads) {
-    const double* c = pad8 + 9 * it;
-    const double x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], x4 = c[4], x5 = c[5], x6 = c[6], x7 = c[7];
-    const double p0 = x0 + x1, p1 = x2 + x3, p2 = x4 + x5, p3 = x6 + x7;
-    const double q0 = p0 + p1, q1 = p2 + p3;
-    const double r = q0 + q1;
-    a1 = sq_acc(x1, x0, a1); a1 = sq_acc(x2, x1, a1); a1 = sq_acc(x3, x2, a1); a1 = sq_acc(x4, x3, a1);
-    a1 = sq_acc(x5, x4, a1); a1 = sq_acc(x6, x5, a1); a1 = sq_acc(x7, x6, a1);
-    a2 = sq_acc(p1, p0, a2); a2 = sq_acc(p2, p1, a2); a2 = sq_acc(p3, p2, a2);
-    a4 = sq_acc(q1, q0, a4);
-    if (it > 0 || has_prev) {
-      double y[8];
-      if (it > 0) {
-        const double* d = c - 9;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) y[q] = d[q];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) y[q] = x[q - 8];
-      }
-      const double pp2 = y[4] + y[5], pp3 = y[6] + y[7];
-      const double qq1 = pp2 + pp3, qq0 = (y[0] + y[1]) + (y[2] + y[3]);
-      a1 = sq_acc(x0, y[7], a1);
-      a2 = sq_acc(p0, pp3, a2);
-      a4 = sq_acc(q0, qq1, a4);
-      a8 = sq_acc(r, qq0 + qq1, a8);
+// Persistent front end: CTA b takes tiles b, b + grid, ...; the raw tile (with its halo) arrives
+// by one bulk copy into a two-stage ring, is offset-subtracted into the two working copies by all
+// threads, and the stage is handed back to the copy engine for the tile after the next before the
+// cluster sums are computed -- two tiles are always in flight per SM.
+constexpr int kAllanStages = 2;
+__global__ void __launch_bounds__(kAllanFastThreads, 1) allan_stream_kernel(const __grid_constant__ AllanLevelParams p) {
+  extern __shared__ __align__(128) double smem[];
+  double* in_buf = smem;                                          // [kAllanStages][kAllanRawLen]
+  double* raw = smem + kAllanStages * kAllanRawLen;               // [kAllanRawLen]
+  double* pad48 = raw + kAllanRawLen;                             // [kAllanPad48]
+  __shared__ AllanTileSmem sm;
+  __shared__ __align__(8) uint64_t full[kAllanStages];
+  const int tid = threadIdx.x;
+  const int64_t tiles = p.nseries * p.chunk_count;
+  auto issue = [&](int64_t tile, int stage) {
+    const int64_t series = tile / p.chunk_count, chunk = tile % p.chunk_count;
+    const double* base = p.level0 ? p.src + series * p.outer_stride : p.src + series * p.src_pitch;
+    const int lead = (chunk != 0) ? kAllanLead : 0;
+    const uint32_t bytes = static_cast<uint32_t>((kAllanChunk + lead) * sizeof(double));
+    mbar_arrive_expect_tx(&full[stage], bytes);
+    bulk_g2s(in_buf + stage * kAllanRawLen + (kAllanLead - lead), base + chunk * kAllanChunk - lead, bytes,
+             &full[stage]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kAllanStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+    for (int s = 0; s < kAllanStages; ++s) {
+      const int64_t tile = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
+      if (tile < tiles) issue(tile, s);
     }
-  }
-  // ---- role B: j = 3, 6, 9 -----------------------------------------------------------------
-  if (jm >= 3) {
-    for (int it = threadIdx.x; it < kAllanChunk / 18; it += kAllanFullThreads) {
-      const double* c = x + 18 * it;
-      double t[6];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) t[q] = (c[3 * q] + c[3 * q + 1]) + c[3 * q + 2];
-      const double s0 = t[0] + t[1], s1 = t[2] + t[3], s2 = t[4] + t[5];
-      const double n0 = s0 + t[2], n1 = t[3] + s2;
-#pragma unroll
-      for (int q = 1; q < 6; ++q) a3 = sq_acc(t[q], t[q - 1], a3);
-      a6 = sq_acc(s1, s0, a6); a6 = sq_acc(s2, s1, a6);
-      a9 = sq_acc(n1, n0, a9);
-      if (it > 0 || has_prev) {
-        // the clusters that end at the left edge: 3, 6 and 9 samples back
-        const double u2 = (c[-3] + c[-2]) + c[-1], u1 = (c[-6] + c[-5]) + c[-4], u0 = (c[-9] + c[-8]) + c[-7];
-        a3 = sq_acc(t[0], u2, a3);
-        a6 = sq_acc(s0, u1 + u2, a6);
-        a9 = sq_acc(n0, (u0 + u1) + u2, a9);
-      }
-    }
-  }
-  // ---- role C: j = 5 and the decade sums ------------------------------------------------------
-  {
-    const int64_t d_lo = c0 / 10;
-    for (int it = threadIdx.x; it < kAllanChunk / 10; it += kAllanFullThreads) {
-      const double* c = x + 10 * it;
-      const double f0 = ((c[0] + c[1]) + (c[2] + c[3])) + c[4];
-      const double f1 = ((c[5] + c[6]) + (c[7] + c[8])) + c[9];
-      a5 = sq_acc(f1, f0, a5);
-      if (it > 0 || has_prev) {
-        const double g1 = ((c[-5] + c[-4]) + (c[-3] + c[-2])) + c[-1];
-        a5 = sq_acc(f0, g1, a5);
-      }
-      if (p.next_len > 0) p.next[series * p.next_len + d_lo + it] = (f0 + f1) + 10.0 * off;
-    }
-  }
-  // ---- role D: j = 7 -----------------------------------------------------------------------------
-  if (jm >= 7) {
-    for (int it = threadIdx.x; it < kAllanChunk / 7; it += kAllanFullThreads) {
-      const double* c = x + 7 * it;
-      const double g = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + c[6]);
-      if (it > 0 || has_prev) {
-        const double gp = ((c[-7] + c[-6]) + (c[-5] + c[-4])) + ((c[-3] + c[-2]) + c[-1]);
-        a7 = sq_acc(g, gp, a7);
-      }
-    }
-  }
-  // ---- block reduction, fixed order -------------------------------------------------------------
-  const double acc[9] = {a1, a2, a3, a4, a5, a6, a7, a8, a9};
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    double v = acc[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 9) {
-    double v = 0.0;
-    for (int w = 0; w < kAllanFullThreads / 32; ++w) v += red[w][threadIdx.x];
-    p.partial[(series * p.chunks + chunk) * 9 + threadIdx.x] = (threadIdx.x < jm) ? v : 0.0;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int stage = it % kAllanStages;
+    const int64_t series = tile / p.chunk_count, chunk = tile % p.chunk_count;
+    const bool has_prev = chunk != 0;
+    mbar_wait(&full[stage], (it / kAllanStages) & 1);
+    const double* in = in_buf + stage * kAllanRawLen;
+    const double off = in[has_prev ? 1 : kAllanLead];
+    {
+      const double2* in2 = reinterpret_cast<const double2*>(in);
+      double2* raw2 = reinterpret_cast<double2*>(raw);
+      double2* pad2 = reinterpret_cast<double2*>(pad48);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int u = tid + q * kAllanFastThreads;
+        if (u < (kAllanLead + kAllanChunk) / 2) {
+          double2 w = in2[u];
+          w.x -= off;
+          w.y -= off;
+          raw2[u] = w;
+          const int ue = u - kAllanLead / 2;
+          if (ue >= 0) pad2[ue + ue / 24] = w;
+        }
+      }
+    }
+    __syncthreads();   // both copies complete; the stage has been consumed
+    if (tid == 0) {
+      const int64_t nxt = tile + static_cast<int64_t>(kAllanStages) * gridDim.x;
+      if (nxt < tiles) {
+        fence_async_smem();
+        issue(nxt, stage);
+      }
+    }
+    allan_tile_compute(p, series, chunk, raw + kAllanLead, pad48, 10.0 * off, sm);
+    // the next pass overwrites raw / pad48: every read of them precedes the last barrier inside
+    // allan_tile_compute; sm.red is rewritten only after two more barriers
   }
 }
 
@@ -313,25 +511,117 @@ struct AllanFinalParams {
   int j_of[128];
 };
 
-__global__ void allan_final_kernel(const __grid_constant__ AllanFinalParams p) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+// One warp per (series, tau): lane l adds the partials of chunks l, l+32, ... in order, then a
+// fixed butterfly -- deterministic, and the chunk partials are read with 32 requests in flight
+// instead of one dependent chain.
+__global__ void __launch_bounds__(128) allan_final_kernel(const __grid_constant__ AllanFinalParams p) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= p.nseries * p.ntau) return;
+  const int lane = threadIdx.x & 31;
   const int64_t series = idx / p.ntau;
   const int i = static_cast<int>(idx % p.ntau);
   const int k = p.level_of[i], j = p.j_of[i];
   const double* part = p.partial[k] + series * p.chunks[k] * 9 + (j - 1);
   double s = 0.0;
-  for (int64_t c = 0; c < p.chunks[k]; ++c) s += part[c * 9];
-  const double m = static_cast<double>(p.m[i]);
-  // avar = 0.5/(nbins-1) * sum (mean[b+1]-mean[b])^2, allan.py:54-57
-  p.avar[series * p.ntau + i] = 0.5 / static_cast<double>(p.nbins[i] - 1) * (s / (m * m));
-  if (series == 0) p.tau[i] = m * p.ts;  // allan.py:58
+  for (int64_t c = lane; c < p.chunks[k]; c += 32) s += part[c * 9];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const double m = static_cast<double>(p.m[i]);
+    // avar = 0.5/(nbins-1) * sum (mean[b+1]-mean[b])^2, allan.py:54-57
+    p.avar[series * p.ntau + i] = 0.5 / static_cast<double>(p.nbins[i] - 1) * (s / (m * m));
+    if (series == 0) p.tau[i] = m * p.ts;  // allan.py:58
+  }
+}
+
+// ---- the short upper levels in one launch ---------------------------------------------------
+// Once a level has at most one chunk, it and every level above it fit in shared memory: one CTA
+// per series keeps the decade sums on chip and walks the remaining levels (direct evaluation:
+// one successive-difference term per thread and step), instead of one launch per level.
+constexpr int kAllanRestThreads = 512;
+struct AllanRestParams {
+  const double* src;     // the first of these levels: x (level0 addressing) or S_k [nseries][len]
+  int64_t len, src_pitch, inner, outer_stride, sample_stride;
+  int level0, levels;    // number of levels handled here
+  int jmax[kAllanMaxLevels];
+  double* partial[kAllanMaxLevels];   // [nseries][1][9] each
+};
+
+__global__ void __launch_bounds__(kAllanRestThreads) allan_rest_kernel(const __grid_constant__ AllanRestParams p) {
+  __shared__ double buf_a[kAllanChunk];        // levels k, k+2, ...
+  __shared__ double buf_b[kAllanChunk / 10];   // levels k+1, k+3, ...
+  __shared__ double red[kAllanRestThreads / 32][9];
+  const int64_t series = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int len = static_cast<int>(p.len);
+  {
+    const double* base;
+    int64_t stride;
+    if (p.level0) {
+      base = p.src + (series / p.inner) * p.outer_stride + (series % p.inner);
+      stride = p.sample_stride;
+    } else {
+      base = p.src + series * p.src_pitch;
+      stride = 1;
+    }
+    for (int e = tid; e < len; e += kAllanRestThreads) buf_a[e] = base[e * stride];
+  }
+  __syncthreads();
+  for (int k = 0; k < p.levels; ++k) {
+    const double* x = (k & 1) ? buf_b : buf_a;
+    double* nx = (k & 1) ? buf_a : buf_b;
+    // the first element cancels in every difference: subtracting it keeps the cluster sums small
+    const double off = x[0];
+    double acc[9];
+#pragma unroll
+    for (int j = 1; j <= 9; ++j) {
+      double a = 0.0;
+      const int nb = len / j;
+      for (int b = tid; b + 1 < nb; b += kAllanRestThreads) {
+        const double* q = x + b * j;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int e = 0; e < j; ++e) {
+          s0 += q[e] - off;
+          s1 += q[j + e] - off;
+        }
+        const double d = s1 - s0;
+        a = fma(d, d, a);
+      }
+      acc[j - 1] = a;
+    }
+    const int nlen = len / 10;
+    if (k + 1 < p.levels) {
+      for (int i = tid; i < nlen; i += kAllanRestThreads) {
+        const double* q = x + i * 10;
+        double s0 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 10; ++e) s0 += q[e];
+        nx[i] = s0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      double v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (tid < 9) {
+      double v = 0.0;
+      for (int w = 0; w < kAllanRestThreads / 32; ++w) v += red[w][tid];
+      p.partial[k][series * 9 + tid] = (tid < p.jmax[k]) ? v : 0.0;
+    }
+    __syncthreads();
+    len = nlen;
+  }
 }
 
 inline int64_t allan_workspace_bytes(int64_t n, int64_t nseries) {
   if (n <= 0 || nseries <= 0) return 16;
   int64_t doubles = 0;
-  const int64_t n1 = n / 10 + 1;
+  const int64_t n1 = (n / 10 + 2) & ~int64_t(1);   // even row pitch
   doubles += 2 * n1 * nseries;  // ping-pong decade sums
   int64_t len = n;
   for (int k = 0; k < kAllanMaxLevels && len > 0; ++k) {
@@ -344,7 +634,7 @@ inline int64_t allan_workspace_bytes(int64_t n, int64_t nseries) {
 // returns 0 on success
 inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, int64_t inner,
                         int64_t outer_stride, int64_t sample_stride, const int64_t* mult, int ntau,
-                        double* avar, double* tau, void* workspace, cudaStream_t s) {
+                        double* avar, double* tau, void* workspace, int sms, cudaStream_t s) {
   AllanFinalParams fp;
   std::memset(&fp, 0, sizeof(fp));
   fp.nseries = nseries;
@@ -371,20 +661,33 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     if (i != ntau) return 1;
   }
   double* ws = static_cast<double*>(workspace);
-  const int64_t n1 = n / 10 + 1;
+  const int64_t n1 = (n / 10 + 2) & ~int64_t(1);   // even row pitch: rows stay 16-byte aligned
   double* buf[2] = {ws, ws + n1 * nseries};
   double* part = ws + 2 * n1 * nseries;
   int64_t len = n;
   const size_t smem = (kAllanChunk + kAllanHalo + 1 + 16) * sizeof(double);
-  const size_t smem_full = (kAllanChunk + kAllanHalo + 1 + kAllanPad8 + 16) * sizeof(double);
+  const size_t smem_full = (kAllanRawLen + kAllanPad48) * sizeof(double);
+  const size_t smem_stream = ((kAllanStages + 1) * kAllanRawLen + kAllanPad48) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(allan_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem)) != cudaSuccess)
       return 2;
-    if (cudaFuncSetAttribute(allan_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_full)) != cudaSuccess)
+    if (cudaFuncSetAttribute(allan_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_full)) != cudaSuccess ||
+        cudaFuncSetAttribute(allan_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_full)) != cudaSuccess ||
+        cudaFuncSetAttribute(allan_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_stream)) != cudaSuccess)
       return 2;
+    // both kernels stage everything through shared memory: ask for the largest carve-out so that
+    // two (fast kernel) / five (tail kernel) CTAs are resident per SM
+    cudaFuncSetAttribute(allan_full_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(allan_full_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(allan_level_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   for (int k = 0; k < levels; ++k) {
@@ -401,16 +704,52 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     lp.chunks = (len + kAllanChunk - 1) / kAllanChunk;
     lp.partial = part;
     lp.jmax = jmax[k];
+    lp.src_pitch = n1;
+    lp.next_pitch = n1;
     fp.partial[k] = part;
     fp.chunks[k] = lp.chunks;
     part += lp.chunks * 9 * nseries;
     if (lp.chunks * nseries >= (int64_t(1) << 31)) return 4;
+    if (len <= kAllanChunk) {   // this level and all above it: one launch, decade sums stay on chip
+      AllanRestParams rp;
+      std::memset(&rp, 0, sizeof(rp));
+      rp.src = lp.src;
+      rp.len = len;
+      rp.src_pitch = n1;
+      rp.inner = inner;
+      rp.outer_stride = outer_stride;
+      rp.sample_stride = sample_stride;
+      rp.level0 = lp.level0;
+      rp.levels = levels - k;
+      int64_t l2 = len;
+      for (int kk = k; kk < levels; ++kk, l2 /= 10) {
+        rp.jmax[kk - k] = jmax[kk];
+        rp.partial[kk - k] = part - lp.chunks * 9 * nseries + (kk - k) * 9 * nseries;
+        fp.partial[kk] = rp.partial[kk - k];
+        fp.chunks[kk] = 1;
+      }
+      allan_rest_kernel<<<static_cast<unsigned>(nseries), kAllanRestThreads, 0, s>>>(rp);
+      break;
+    }
     // full chunks (every cluster complete, next-level decades complete) take the fast kernel
     const int64_t full = len / kAllanChunk;
     if (full > 0) {
       lp.chunk_first = 0;
       lp.chunk_count = full;
-      allan_full_kernel<<<static_cast<unsigned>(full * nseries), kAllanFullThreads, smem_full, s>>>(lp);
+      const int64_t tiles = full * nseries;
+      const bool contiguous = !lp.level0 || sample_stride == 1;
+      // the bulk copies need 16-byte aligned rows: always true for the decade sums (even pitch),
+      // for the caller's series if the base and the row stride allow it
+      const bool aligned = !lp.level0 || (inner == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                                          (outer_stride & 1) == 0);
+      if (contiguous && aligned) {
+        const int64_t grid = tiles < sms ? tiles : sms;
+        allan_stream_kernel<<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
+      } else if (contiguous) {
+        allan_full_kernel<true><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
+      } else {
+        allan_full_kernel<false><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
+      }
     }
     if (lp.chunks > full) {   // the ragged last chunk
       lp.chunk_first = full;
@@ -420,7 +759,7 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     len /= 10;
   }
   const int64_t total = nseries * ntau;
-  allan_final_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(fp);
+  allan_final_kernel<<<static_cast<unsigned>((total + 3) / 4), 128, 0, s>>>(fp);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

@@ -14,6 +14,7 @@
 #include "noise_kernel.cuh"
 #include "pathgen_host.h"
 #include "psd_kernel.cuh"
+#include "gps_kernel.cuh"
 #include "stats_kernel.cuh"
 
 using namespace b2ins;
@@ -86,6 +87,10 @@ void layout_strides(int layout, int64_t runs, int64_t n, int64_t* sr, int64_t* s
     *sr = n * 3;
     *st = 3;
     *sc = 1;
+  } else if (layout == B2INS_LAYOUT_CHANNEL_MAJOR) {
+    *sr = n * 3;
+    *st = 1;
+    *sc = n;
   } else {
     *sr = 1;
     *st = 3 * runs;
@@ -328,7 +333,7 @@ int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gy
                         double* gyro, double* accel, double* z_dump, void* stream) {
   ARG_CHECK(fs > 0.0, "fs must be positive");
   ARG_CHECK(runs >= 0 && n >= 0, "runs and n must be non-negative");
-  ARG_CHECK(layout == 0 || layout == 1, "layout must be B2INS_LAYOUT_*");
+  ARG_CHECK(layout >= 0 && layout <= 2, "layout must be B2INS_LAYOUT_*");
   if (runs == 0 || n == 0) return B2INS_OK;
   ARG_CHECK(ref_gyro && ref_accel && gyro_err && accel_err && gyro && accel, "null buffer");
   ARG_CHECK(n < (int64_t(1) << 32), "n must be < 2^32");
@@ -385,6 +390,36 @@ int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gy
   }
   imu_noise_kernel<<<static_cast<unsigned>(runs * p.nseg), kNoiseThreads, 0, s>>>(p);
   if (scratch) CU_CHECK(cudaFreeAsync(scratch, s));
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+int b2ins_gps_noise_f64(int64_t runs, int64_t m, const double* ref_gps, const double* stdp,
+                        const double* stdv, int gps_type, uint64_t seed, int64_t run_offset,
+                        double* gps, void* stream) {
+  ARG_CHECK(runs >= 0 && m >= 0, "runs and m must be non-negative");
+  ARG_CHECK(gps_type == 0 || gps_type == 1, "gps_type must be 0 (LLA) or 1 (xyz)");
+  if (runs == 0 || m == 0) return B2INS_OK;
+  ARG_CHECK(ref_gps && stdp && stdv && gps, "null buffer");
+  ARG_CHECK(m < (int64_t(1) << 32), "m must be < 2^32");
+  GpsParams p;
+  p.m = m;
+  p.runs = runs;
+  p.run_offset = run_offset;
+  p.ref = ref_gps;
+  p.out = gps;
+  for (int i = 0; i < 3; ++i) {
+    p.stdp[i] = stdp[i];
+    p.stdv[i] = stdv[i];
+  }
+  p.k0 = static_cast<uint32_t>(seed);
+  p.k1 = static_cast<uint32_t>(seed >> 32);
+  p.gps_type = gps_type;
+  const int64_t total = runs * m;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  gps_noise_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }
@@ -756,7 +791,7 @@ int b2ins_allan_f64(double fs, int64_t n, int64_t nseries, const double* x, int6
   ARG_CHECK(x && avar && tau && workspace, "null buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rc = allan_launch(fs, n, nseries, x, inner, outer_stride, sample_stride, mult, ntau,
-                              avar, tau, workspace, s);
+                              avar, tau, workspace, sm_count(), s);
   if (rc != 0) return fail(B2INS_ERR_CUDA, "allan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import LAYOUT_RUN_MAJOR, LAYOUT_TIME_MAJOR  # noqa: F401
+from ._lib import LAYOUT_RUN_MAJOR, LAYOUT_TIME_MAJOR, LAYOUT_CHANNEL_MAJOR  # noqa: F401
 
 
 def _require_cuda():
@@ -96,11 +96,13 @@ def free_integration_odo(ref_frame, fs, gyro, odo, ini, earth_rot=True, layout=L
 def imu_noise(fs, runs, ref_gyro, ref_accel, gyro_err, accel_err, seed, run_offset=0,
               vib_gyro=None, vib_accel=None, layout=LAYOUT_RUN_MAJOR, dump_z=False):
     """K1.  ref_gyro/ref_accel: CUDA f64 [n,3]; *_err: imu_model dicts.
-    Returns gyro, accel ([R,n,3] or [n,3,R]) and, if dump_z, z [R,n,12]."""
+    Returns gyro, accel ([R,n,3], [n,3,R] or, LAYOUT_CHANNEL_MAJOR, [R,3,n]) and, if dump_z,
+    z [R,n,12]."""
     _require_cuda()
     lib = _lib.load()
     n = ref_gyro.shape[0]
-    shape = (runs, n, 3) if layout == LAYOUT_RUN_MAJOR else (n, 3, runs)
+    shape = {LAYOUT_RUN_MAJOR: (runs, n, 3), LAYOUT_TIME_MAJOR: (n, 3, runs),
+             LAYOUT_CHANNEL_MAJOR: (runs, 3, n)}[layout]
     gyro = torch.empty(shape, dtype=torch.float64, device=ref_gyro.device)
     accel = torch.empty_like(gyro)
     z = torch.empty((runs, n, 12), dtype=torch.float64, device=ref_gyro.device) if dump_z else None
@@ -112,6 +114,20 @@ def imu_noise(fs, runs, ref_gyro, ref_accel, gyro_err, accel_err, seed, run_offs
         ctypes.byref(vg), ctypes.byref(va), int(seed), int(run_offset), layout,
         _ptr(gyro), _ptr(accel), _ptr(z), _stream()))
     return (gyro, accel, z) if dump_z else (gyro, accel)
+
+
+def gps_noise(runs, ref_gps, gps_err, gps_type, seed, run_offset=0):
+    """K6: pathgen.gps_gen for `runs` runs.  ref_gps: CUDA f64 [m,6]; gps_err {'stdp','stdv'} [3];
+    gps_type 0 (LLA, ref_frame 0) or 1 (xyz).  Returns [R,m,6]."""
+    _require_cuda()
+    lib = _lib.load()
+    m = ref_gps.shape[0]
+    out = torch.empty((runs, m, 6), dtype=torch.float64, device=ref_gps.device)
+    stdp = np.ascontiguousarray(np.broadcast_to(np.asarray(gps_err['stdp'], dtype=np.float64), (3,)))
+    stdv = np.ascontiguousarray(np.broadcast_to(np.asarray(gps_err['stdv'], dtype=np.float64), (3,)))
+    _lib.check(lib.b2ins_gps_noise_f64(runs, m, _ptr(ref_gps), _lib.host_ptr(stdp), _lib.host_ptr(stdv),
+                                       int(gps_type), int(seed), int(run_offset), _ptr(out), _stream()))
+    return out
 
 
 class McResult:

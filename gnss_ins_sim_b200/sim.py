@@ -324,6 +324,7 @@ class Sim(object):
         self._nav_end = np.concatenate([traj['ref_att'][-1], traj['ref_pos'][-1], traj['ref_vel'][-1]])
         self._nav_cache = None
         self._dev_cache = None
+        self._ref_gps_dev = None
 
     @property
     def _nav(self):
@@ -371,6 +372,8 @@ class Sim(object):
             if 'ref_odo' not in self._traj:
                 raise ValueError('imu.odo is on but the trajectory has no ref_odo')
             self.data['odo'] = LazyRuns(self, 'odo', R)
+        if getattr(self.imu, 'gps', False) and 'ref_gps' in self._traj:
+            self.data['gps'] = LazyRuns(self, 'gps', R)     # pathgen.gps_gen per run (ins_sim.py:497-500)
         if self.algo is not None:
             for i, a in enumerate(self.algo):
                 if isinstance(a, FreeIntegration):     # incl. the odometer variant
@@ -476,14 +479,15 @@ class Sim(object):
                 self.data[out] = lazy
         self.data['att_quat'] = DerivedRuns(self.data['att_euler'], euler2quat_zyx)
 
-    def _noise_block(self, r0, r1):
-        """K1 for global-in-experiment runs [r0, r1): CUDA gyro, accel [r1-r0, n, 3]."""
+    def _noise_block(self, r0, r1, layout=engine.LAYOUT_RUN_MAJOR):
+        """K1 for global-in-experiment runs [r0, r1): CUDA gyro, accel [r1-r0, n, 3]
+        ([r1-r0, 3, n] with LAYOUT_CHANNEL_MAJOR)."""
         d = self._dev
         vib_gyro, vib_acc = self._vib_pair(r1 - r0, r0)
         return engine.imu_noise(self.fs[0], r1 - r0, d['ref_gyro'], d['ref_accel'],
                                 self.imu.gyro_err, self.imu.accel_err, self.seed,
                                 run_offset=self.run_base + r0, vib_gyro=vib_gyro,
-                                vib_accel=vib_acc)
+                                vib_accel=vib_acc, layout=layout)
 
     def _run_allan(self, i, algo):
         name = self.algo_name(i)
@@ -496,8 +500,9 @@ class Sim(object):
         tau_all, ada, adg = None, {}, {}
         for r0 in range(0, R, block):
             r1 = min(R, r0 + block)
-            gyro, accel = self._noise_block(r0, r1)
-            tau, a, g = algo.run_batch(self.fs[0], accel, gyro)
+            # every channel a contiguous series: K4 then streams them with bulk copies
+            gyro, accel = self._noise_block(r0, r1, engine.LAYOUT_CHANNEL_MAJOR)
+            tau, a, g = algo.run_batch(self.fs[0], accel, gyro, channel_major=True)
             for r in range(r0, r1):
                 ada['%s_%d' % (name, r)] = a[r - r0]
                 adg['%s_%d' % (name, r)] = g[r - r0]
@@ -566,6 +571,11 @@ class Sim(object):
                 if not ai:
                     raise KeyError('odo histories are produced with the free_integration_odo plugin')
                 self._history((ai[0], 'pos'), run)
+            elif name == 'gps':
+                if getattr(self, '_ref_gps_dev', None) is None:
+                    self._ref_gps_dev = engine.to_device(self._traj['ref_gps'])
+                hist['gps'] = engine.gps_noise(r1 - r0, self._ref_gps_dev, self.imu.gps_err, self.ref_frame,
+                                               self.seed, run_offset=r0).cpu().numpy()
             else:
                 gyro, accel = self._noise_block(r0, r1)
                 hist.update({'gyro': gyro.cpu().numpy(), 'accel': accel.cpu().numpy()})

@@ -15,11 +15,13 @@
  *   - entry points ending in _host take HOST pointers, do the H2D / D2H copies
  *     themselves on an internal stream and return when the results are in the
  *     caller's buffers (this is what a ctypes / cgo / JNI stub binds first).
- *   - series of per-run 3-vectors x(run r, sample t, component c) use one of two
+ *   - series of per-run 3-vectors x(run r, sample t, component c) use one of these
  *     layouts:
  *       B2INS_LAYOUT_RUN_MAJOR  [R][n][3]  -- run r is exactly the reference's
  *                                             (n,3) C-contiguous numpy array
  *       B2INS_LAYOUT_TIME_MAJOR [n][3][R]  -- device-native for lanes_per_run = 1
+ *       B2INS_LAYOUT_CHANNEL_MAJOR [R][3][n] -- every channel of every run a contiguous
+ *                                             series (K1 output only: what K4 reads best)
  *   - "ini" is [ini_sets][ini_rows] (ini_rows = 9: lat,lon,alt [rad,rad,m], body
  *     velocity [m/s], yaw,pitch,roll [rad]; ini_rows = 10 adds a gravity override
  *     [m/s^2]) -- the transpose of FreeIntegration's ini_pos_vel_att
@@ -44,6 +46,7 @@ extern "C" {
 
 #define B2INS_LAYOUT_RUN_MAJOR 0
 #define B2INS_LAYOUT_TIME_MAJOR 1
+#define B2INS_LAYOUT_CHANNEL_MAJOR 2
 
 #define B2INS_VIB_NONE 0
 #define B2INS_VIB_RANDOM 1     /* pathgen.py:486-489 / :549-552 */
@@ -265,6 +268,18 @@ int64_t b2ins_psd_workspace_bytes(int64_t n, int64_t runs);
 int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int table_len,
                          const double* freq, const double* sxx3, uint64_t seed,
                          int64_t run_offset, double* series, void* workspace, void* stream);
+
+/* ---- K6: GPS measurement generator ---------------------------------------------------
+ * Replaces pathgen.gps_gen (gnss_ins_sim/pathgen/pathgen.py:596-625) and its call in loop A
+ * (gnss_ins_sim/sim/ins_sim.py:497-500) for `runs` runs at once:
+ *   gps[r][k] = ref_gps[k] + (pos_err, stdv) * N(0,1),   Philox draws (k, 24..26, run_offset + r).
+ * ref_gps [m][6] (device): position (LLA rad/rad/m if gps_type 0 = ref_frame 0, xyz m if 1) and
+ * NED velocity, as path_gen's 'gps' columns 1..6.  stdp / stdv: host [3], metres and m/s; with
+ * gps_type 0 the horizontal position sigmas are converted to radians at ref_gps[0], like the
+ * reference.  gps [runs][m][6] (device). */
+int b2ins_gps_noise_f64(int64_t runs, int64_t m, const double* ref_gps, const double* stdp,
+                        const double* stdv, int gps_type, uint64_t seed, int64_t run_offset,
+                        double* gps, void* stream);
 
 /* ---- host: true-trajectory generator -----------------------------------------------
  * Replaces pathgen.path_gen (gnss_ins_sim/pathgen/pathgen.py:26-329, with

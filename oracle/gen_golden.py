@@ -237,6 +237,44 @@ def gen_philox_odo(ref_frame, R=6, seed=4711):
                         accel_b_corr=imu.accel_err['b_corr'], accel_vrw=imu.accel_err['vrw'], **out)
 
 
+def gen_gps(ref_frame, R=4, seed=2024):
+    """IMU(gps=True) at 10 Hz: after the 8 IMU blocks of a run the reference draws the GPS position
+    and velocity noise, two (m, 3) blocks (pathgen.py:622-623 via ins_sim.py:497-500); they are
+    served from the b2ins stream (draws 24..26)."""
+    csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
+    gps_err = {'stdp': np.array([5.0, 5.0, 7.0]), 'stdv': np.array([0.05, 0.05, 0.05])}
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=True, gps_opt=gps_err)
+    sim = ins_sim.Sim([100.0, 10.0, 0.0], csv, ref_frame=ref_frame, imu=imu, algorithm=None)
+    n, m = 1000, 100
+    run_ids = np.arange(R) + 5
+    z = onp.noise_normals(n, run_ids, seed)
+    zg = onp.gps_normals(m, run_ids, seed)
+    q = RandnQueue()
+    for r in range(R):
+        for gm, w in ((z['acc_gm'], z['acc_w']), (z['gyr_gm'], z['gyr_w'])):
+            for i in range(3):
+                blk = np.full((n, 3), np.nan)
+                blk[:, i] = gm[r, :, i]
+                q.push(blk)
+            q.push(w[r])
+        q.push(zg[r, :, 0:3])
+        q.push(zg[r, :, 3:6])
+    real = np.random.randn
+    np.random.randn = q
+    try:
+        sim.run(R)
+    finally:
+        np.random.randn = real
+    assert not q.q
+    d = sim.dmgr
+    assert d.ref_gps.data.shape == (m, 6)
+    np.savez_compressed(os.path.join(OUT, 'gps_90deg_rf%d.npz' % ref_frame),
+                        ref_frame=ref_frame, seed=seed, run_ids=run_ids, stdp=gps_err['stdp'],
+                        stdv=gps_err['stdv'], ref_gps=d.ref_gps.data, gps_time=d.gps_time.data,
+                        gps_visibility=d.gps_visibility.data,
+                        gps=np.stack([d.gps.data[i] for i in range(R)]))
+
+
 def gen_traj(tag, motion, fs, ref_frame):
     csv = os.path.join(MOTION, motion)
     imu = fresh_imu('low-accuracy')
@@ -343,6 +381,8 @@ def main():
                          'gyro': '[6 5 4]d-0.5Hz-sinusoidal'})
     gen_philox_odo(1)
     gen_philox_odo(0)
+    gen_gps(0)
+    gen_gps(1)
     gen_traj('90deg_turn_100hz_rf1', 'motion_def-90deg_turn.csv', 100.0, 1)
     gen_traj('90deg_turn_100hz_rf0', 'motion_def-90deg_turn.csv', 100.0, 0)
     gen_pathgen()

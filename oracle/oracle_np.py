@@ -243,6 +243,30 @@ def free_integration_odo(ref_frame, fs, gyro, odo, ini, earth_rot=True):
     return att, pos, vel
 
 
+def gps_normals(m, run_ids, seed):
+    """[R, m, 6] normals of pathgen.gps_gen: pairs (k, PAIR_GPS + j), j = 0..2, flattened."""
+    run_ids = np.asarray(run_ids, dtype=np.uint64)
+    k = np.arange(m, dtype=np.uint64)[None, :]
+    z = np.empty((run_ids.size, m, 6))
+    for j in range(3):
+        z0, z1 = normal_pair(k, PAIR_GPS + j, run_ids[:, None], seed)
+        z[:, :, 2 * j] = z0
+        z[:, :, 2 * j + 1] = z1
+    return z
+
+
+def gps_gen(ref_gps, gps_err, gps_type, z):
+    """pathgen.gps_gen, pathgen.py:596-625.  ref_gps [m, 6]; z [R, m, 6] -> [R, m, 6]."""
+    ref_gps = np.asarray(ref_gps, dtype=np.float64)
+    pos_err = np.array(gps_err['stdp'], dtype=np.float64).copy()
+    if gps_type == 0:
+        rm, rn, _, _, cl = geo_param(ref_gps[0, 0], ref_gps[0, 2])
+        pos_err[0] = pos_err[0] / rm
+        pos_err[1] = pos_err[1] / rn / cl
+    sd = np.concatenate([pos_err, np.asarray(gps_err['stdv'], dtype=np.float64)])
+    return ref_gps[None, :, :] + sd[None, None, :] * z
+
+
 def odo_normals(n, run_ids, seed):
     """[R, n] normals of pathgen.odo_gen: z0 of the pair (t, PAIR_ODO)."""
     run_ids = np.asarray(run_ids, dtype=np.uint64)
@@ -274,6 +298,7 @@ PAIR_VIB = 6        # +axis : (accel random vib, gyro random vib)
 PAIR_PHASE = 9      # +axis, t = 0xFFFFFFFF : sinusoidal gyro-vib phase uniforms
 PAIR_ODO = 12       # odometer white noise (z0)
 PAIR_PSD = 16       # +3*sensor+axis (sensor 0 accel, 1 gyro), t = bin index: PSD phases (z0)
+PAIR_GPS = 24       # +j, t = GPS sample: (pos0, pos1), (pos2, vel0), (vel1, vel2)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

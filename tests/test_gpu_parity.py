@@ -109,6 +109,11 @@ def test_k1_noise_vs_reference_injection(eng, tag):
                            int(g['seed']), run0, _vib(g, 'vib_gyro'), _vib(g, 'vib_acc'),
                            layout=1)
     assert torch.equal(g2.permute(2, 0, 1), gyro) and torch.equal(a2.permute(2, 0, 1), accel)
+    # and so does CHANNEL_MAJOR ([R][3][n]: every channel a contiguous series, K4's input)
+    g3, a3 = eng.imu_noise(float(g['fs']), R, _dev(g['ref_gyro']), _dev(g['ref_accel']), ge, ae,
+                           int(g['seed']), run0, _vib(g, 'vib_gyro'), _vib(g, 'vib_acc'),
+                           layout=2)
+    assert torch.equal(g3.permute(0, 2, 1), gyro) and torch.equal(a3.permute(0, 2, 1), accel)
 
 
 def _ref_nav(g):

@@ -106,6 +106,21 @@ def test_k4_allan_millions_of_samples(eng):
     assert_close(tau.cpu().numpy(), t, 1e-15, 0.0, 'tau')
 
 
+@pytest.mark.parametrize('n', [200004, 150001])
+def test_k4_allan_contiguous_series_both_front_ends(eng, n):
+    """Contiguous series: even n keeps every row 16-byte aligned (persistent bulk-copy front end,
+    several tiles per CTA: 8 x 39 tiles on 148 SMs), odd n does not (per-thread loads)."""
+    rng = np.random.RandomState(n % 1000)
+    nser, fs = 8, 200.0
+    x = 3.7 + 1e-2 * rng.randn(nser, n) + np.cumsum(1e-5 * rng.randn(nser, n), axis=1)
+    avar, tau = eng.allan(fs, eng.to_device(x), n, nser)
+    avar = avar.cpu().numpy()
+    for r in range(nser):
+        o, t = oracle_c.allan_var(np.ascontiguousarray(x[r]), fs)
+        assert_close(avar[r], o, 1e-9, 0.0, 'avar %d' % r)
+    assert_close(tau.cpu().numpy(), t, 1e-15, 0.0, 'tau')
+
+
 def test_large_ensemble_properties(eng):
     """BASELINE-size ensembles without an oracle: (i) two disjoint halves of 2^16 runs have
     statistically identical error statistics, (ii) end-point std grows like the white-noise

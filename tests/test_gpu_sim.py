@@ -1,11 +1,13 @@
 """GPU tests of the host-side mirror of the reference interface: the FreeIntegration / Allan
 plugins through the reference's plugin protocol and the Sim facade, against the reference's
 golden vectors."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle_np as onp
-from conftest import load_golden, assert_close, wrap_pi
+from conftest import GOLDEN, load_golden, assert_close, wrap_pi
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip('torch')
@@ -188,3 +190,27 @@ def test_odometer_variant_matches_reference(gpu, rf):
     assert_close(sim.get_data(['odo'])[0][3], g['odo'][3], 1e-12, 1.0, 'odo history')
     assert_close(sim.get_data(['pos'])[0]['algo0_4'], g['pos'][4], 1e-9, 1.0 if rf == 1 else 1e-7, 'pos hist')
     assert_close(sim.get_data(['accel'])[0][1], g['accel'][1], 1e-12, 1.0, 'accel history')
+
+
+@pytest.mark.parametrize('rf', [0, 1])
+def test_gps_measurements_match_reference(gpu, rf):
+    """K6 (pathgen.gps_gen for all runs) against the reference fed the same normals, directly and
+    as Sim's per-run 'gps' data with the trajectory generated from the motion definition."""
+    from gnss_ins_sim_b200 import engine, imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    g = load_golden('gps_90deg_rf%d.npz' % rf)
+    R, m, _ = g['gps'].shape
+    err = {'stdp': g['stdp'], 'stdv': g['stdv']}
+    out = engine.gps_noise(R, engine.to_device(g['ref_gps']), err, rf, int(g['seed']),
+                           run_offset=int(g['run_ids'][0])).cpu().numpy()
+    scale = np.array([1e-6, 1e-6, 1.0, 1.0, 1.0, 1.0]) if rf == 0 else 1.0
+    assert_close(out, g['gps'], 1e-12, scale, 'gps')
+    assert engine.gps_noise(0, engine.to_device(g['ref_gps']), err, rf, 1).shape == (0, m, 6)
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=True, gps_opt=err)
+    sim = Sim([100.0, 10.0, 0.0], os.path.join(GOLDEN, 'motion_def-90deg_turn.csv'), ref_frame=rf, imu=imu,
+              algorithm=None, seed=int(g['seed']))
+    sim.run(int(g['run_ids'][-1]) + 1)
+    assert_close(sim.get_data(['ref_gps'])[0], g['ref_gps'], 1e-12, scale, 'ref_gps')
+    assert_close(sim.get_data(['gps_time'])[0], g['gps_time'], 1e-12, 1.0, 'gps_time')
+    r = int(g['run_ids'][2])
+    assert_close(sim.get_data(['gps'])[0][r], g['gps'][2], 1e-12, scale, 'gps history')

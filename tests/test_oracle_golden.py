@@ -135,3 +135,16 @@ def test_odometer_variant_oracle(rf):
     assert_close(att, g['att'], 1e-10, what='att')
     assert_close(pos, g['pos'], 1e-10, what='pos')
     assert_close(vel, g['vel'], 1e-10, what='vel')
+
+
+@pytest.mark.parametrize('rf', [0, 1])
+def test_gps_gen_oracle(rf):
+    """gps_gen restatement == pathgen.gps_gen (pathgen.py:596-625) fed the same normals."""
+    g = load_golden('gps_90deg_rf%d.npz' % rf)
+    R, m, _ = g['gps'].shape
+    z = onp.gps_normals(m, g['run_ids'], int(g['seed']))
+    out = onp.gps_gen(g['ref_gps'], {'stdp': g['stdp'], 'stdv': g['stdv']}, rf, z)
+    assert np.array_equal(out, g['gps'])
+    # the metre -> radian conversion really happened (LLA) / did not (xyz)
+    sd = (out - g['ref_gps'][None]).std(axis=(0, 1))
+    assert (sd[0] < 1e-5) == (rf == 0) and abs(sd[2] / 7.0 - 1) < 0.2 and abs(sd[4] / 0.05 - 1) < 0.2

@@ -42,6 +42,7 @@ def emit(**kw):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ''
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -56,7 +57,7 @@ def main():
          for rf in (0, 1)}
 
     # ---- K12 fused Monte-Carlo ---------------------------------------------------------
-    for rf in (1, 0):
+    for rf in ((1, 0) if only in ('', 'K12') else ()):
         gg = g[rf]
         nav = np.concatenate([gg['ref_att'], gg['ref_pos'], gg['ref_vel']], axis=1)
         n = nav.shape[0]
@@ -73,8 +74,8 @@ def main():
 
     # ---- K2 fed-noise (120 B per run-step: 48 read + 72 written) -------------------------
     gg = g[1]
-    for layout, runs, n, lanes in ((0, 4096, 1000, 0), (0, 32768, 500, 8), (1, 65536, 500, 1),
-                                   (1, 262144, 250, 1)):
+    for layout, runs, n, lanes in (((0, 4096, 1000, 0), (0, 32768, 500, 8), (1, 65536, 500, 1),
+                                    (1, 262144, 250, 1)) if only in ('', 'K2') else ()):
         shape = (runs, n, 3) if layout == 0 else (n, 3, runs)
         gyro = torch.randn(shape, dtype=torch.float64, device='cuda') * 0.01
         accel = torch.randn(shape, dtype=torch.float64, device='cuda') * 0.1
@@ -90,7 +91,7 @@ def main():
 
     # ---- K1 materialised noise (48 B written per run-step) --------------------------------
     rg = torch.zeros((4000, 3), dtype=torch.float64, device='cuda')
-    for runs in (1024, 8192):
+    for runs in ((1024, 8192) if only in ('', 'K1') else ()):
         ms = timed(lambda: engine.imu_noise(100.0, runs, rg, rg, MID_G, MID_A, 1), reps=3)
         rate = runs * 4000 / (ms * 1e-3)
         emit(kernel='K1 imu_noise_kernel', runs=runs, n=4000, ms=ms, run_steps_per_s=rate,
@@ -98,14 +99,14 @@ def main():
              dfma_slots_per_run_step=dfma.value / rate)
 
     # ---- K3 statistics (72 B per run read twice) -------------------------------------------
-    for runs in (1000, 1000000):
+    for runs in ((1000, 1000000) if only in ('', 'K3') else ()):
         err = torch.randn((runs, 9), dtype=torch.float64, device='cuda')
         ms = timed(lambda: engine.error_stats(err), reps=5)
         emit(kernel='K3 error_stats', runs=runs, ms=ms, alg_gbs=runs * 72 * 2 / ms / 1e6,
              hbm_frac=runs * 72 * 2 / ms / 1e6 / hbm)
 
     # ---- K4 Allan (8 B per sample read once + 0.8 B decade sums) ---------------------------
-    for nser, n, inner in ((96, 2000000, 1), (32, 2000000, 3), (6, 14400000, 3)):
+    for nser, n, inner in (((96, 2000000, 1), (32, 2000000, 3), (6, 14400000, 3)) if only in ('', 'K4') else ()):
         x = torch.randn(nser * n, dtype=torch.float64, device='cuda')
         if inner == 1:
             fn = lambda: engine.allan(400.0, x, n, nser)                                   # noqa: E731
@@ -120,7 +121,7 @@ def main():
     # ---- K5 PSD series ----------------------------------------------------------------------
     tab = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'psd.npz')))
     vib = {'type': 'psd', 'freq': tab['freq_a'], 'x': tab['sxx_a'], 'y': tab['sxx_a'], 'z': tab['sxx_a']}
-    for runs, n in ((64, 1000), (64, 40000)):
+    for runs, n in (((64, 1000), (64, 40000)) if only in ('', 'K5') else ()):
         ms = timed(lambda: engine.psd_series(200.0, n, runs, 0, vib, 1), reps=3)
         emit(kernel='K5 psd_series', runs=runs, n=n, ms=ms, series_per_s=runs * 3 / (ms * 1e-3))
 
