@@ -62,10 +62,25 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
   }
   const double off = base[lo * stride];
   // P[i] = sum_{q<i} (x[lo+q] - off), i = 0..cnt ; stored at tile[i]
-  constexpr int kPer = (kAllanChunk + kAllanHalo + kAllanThreads - 1) / kAllanThreads;  // 20
+  // elements per thread in the serial part of the scan: odd, so that the threads of a warp walk
+  // shared memory with an odd stride (no bank conflicts)
+  constexpr int kPer = ((kAllanChunk + kAllanHalo + kAllanThreads - 1) / kAllanThreads) | 1;  // 21
   // coalesced load into the tile (raw values), then a per-thread serial scan of kPer
   // consecutive elements + block scan of the thread totals
-  for (int i = threadIdx.x; i < cnt; i += kAllanThreads) tile[1 + i] = base[(lo + i) * stride] - off;
+  {
+    // every load is issued before the first store (kPer independent requests in flight per thread)
+    double v[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = threadIdx.x + q * kAllanThreads;
+      v[q] = (i < cnt) ? base[(lo + i) * stride] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = threadIdx.x + q * kAllanThreads;
+      if (i < cnt) tile[1 + i] = v[q] - off;
+    }
+  }
   if (threadIdx.x == 0) tile[0] = 0.0;
   __syncthreads();
   const int b0 = threadIdx.x * kPer;
@@ -143,39 +158,34 @@ __global__ void __launch_bounds__(kAllanThreads) allan_level_kernel(const __grid
 
 // ---- fast path: FULL chunks ---------------------------------------------------------------
 // A full chunk holds an integer number of clusters of every size (5040 = 2 lcm(1..10)), so the
-// cluster sums are built hierarchically IN REGISTERS, without bound checks, by four kinds of work
-// items (23 warps):
-//   A1 (105 items of 48 samples, 4 warps): j = 2, 4, 8   (pairs, pairs of pairs, ...)
-//   A2 (280 items of 18 samples, 9 warps): j = 3, 6, 9   (triples, pairs / triples of triples)
-//   C1 (120 items of 42 samples, 4 warps): j = 1, 7
-//   C2 (168 items of 30 samples, 6 warps): j = 5 and the decade sums that feed the next level
-// (~9 FP64 instructions per sample in all).  An item is read with 128-bit shared-memory loads;
-// they are conflict-free when the item pitch is an odd number of 16-byte units: 9, 21 and 15 for
-// A2, C1 and C2 on the raw tile, while A1 (24 units) reads a copy padded 48 -> 50 doubles.  The
-// difference that straddles the left edge of an item uses the neighbour's last cluster sums,
-// exchanged through shared memory (the halo for item 0).  Two front ends fill the two copies:
-//   allan_stream_kernel  contiguous, 16-byte aligned series: persistent CTA per SM, the raw tile
-//                        arrives by one TMA bulk copy per tile, two tiles in flight (mbarriers);
+// cluster sums are built hierarchically IN REGISTERS, without bound checks, by three kinds of work
+// items (16 warps; every sample is read from shared memory once per kind):
+//   X (105 items of 48 samples, 4 warps): j = 2, 4, 8      (pairs, pairs of pairs, ...)
+//   Y (280 items of 18 samples, 9 warps): j = 1, 3, 6, 9   (triples, pairs / triples of triples)
+//   C ( 72 items of 70 samples, 3 warps): j = 5, 7 and the decade sums that feed the next level
+// (~10 FP64 instructions per sample in all).  An item is read with 128-bit shared-memory loads;
+// they are conflict-free when the item pitch is an odd number of 16-byte units: 9 and 35 for Y and
+// C, which read the raw tile where the copy engine put it and subtract the tile offset in
+// registers, while X (24 units) reads a copy padded 48 -> 50 doubles, offset-subtracted when it is
+// made.  The difference that straddles the left edge of an item is formed from the (at most 9)
+// samples to the left of the item, which are in shared memory too (the halo for item 0): no
+// exchange between threads, no barrier.  Two front ends:
+//   allan_stream_kernel  contiguous, 16-byte aligned series: persistent CTA per SM; the raw tile
+//                        arrives by one TMA bulk copy into a three-slot ring (two tiles in
+//                        flight behind the one being computed), the padded copy and the block
+//                        reduction are double-buffered: ONE __syncthreads per tile;
 //   allan_full_kernel    any stride / alignment: per-thread loads, one tile per CTA.
 // The prefix-sum kernel above remains the path for the ragged last chunk of a series.
-constexpr int kAllanItemsA1 = kAllanChunk / 48;   // 105
-constexpr int kAllanItemsA2 = kAllanChunk / 18;   // 280
-constexpr int kAllanItemsC1 = kAllanChunk / 42;   // 120
-constexpr int kAllanItemsC2 = kAllanChunk / 30;   // 168
-constexpr int kAllanPad48 = kAllanItemsA1 * 50;   // 5250
-constexpr int kAllanWarpsA1 = 4, kAllanWarpsA2 = 9, kAllanWarpsC1 = 4, kAllanWarpsC2 = 6;
-constexpr int kAllanFastWarps = kAllanWarpsA1 + kAllanWarpsA2 + kAllanWarpsC1 + kAllanWarpsC2;   // 23
-constexpr int kAllanFastThreads = 32 * kAllanFastWarps;   // 736
+constexpr int kAllanItemsX = kAllanChunk / 48;    // 105
+constexpr int kAllanItemsY = kAllanChunk / 18;    // 280
+constexpr int kAllanItemsC = kAllanChunk / 70;    // 72
+constexpr int kAllanWarpsX = 4, kAllanWarpsY = 9, kAllanWarpsC = 3;
+constexpr int kAllanFastWarps = kAllanWarpsX + kAllanWarpsY + kAllanWarpsC;   // 16
+constexpr int kAllanFastThreads = 32 * kAllanFastWarps;   // 512
 constexpr int kAllanLead = kAllanHalo + 1;        // 10: chunk element e lives at raw[10 + e]
 constexpr int kAllanRawLen = 5056;                // >= 10 + 5040, a multiple of 2
-
-struct AllanTileSmem {
-  double last_a1[kAllanItemsA1][3];
-  double last_a2[kAllanItemsA2][3];
-  double last_c1[kAllanItemsC1];
-  double last_c2[kAllanItemsC2];
-  double red[kAllanFastWarps][4];
-};
+constexpr int kAllanPadLead = 12;                 // halo element -k lives at pad[-2 - k]
+constexpr int kAllanPadLen = kAllanPadLead + kAllanItemsX * 50 + 2;   // 5264
 
 __device__ __forceinline__ double sq_acc(double a, double b, double acc) {
   const double d = a - b;
@@ -206,22 +216,35 @@ __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, dou
   return t;
 }
 
-// One tile, both copies in shared memory (offset-subtracted): x[e], e in [-9, 5040), and pad
-// (element e at e + 2 (e / 48)).  Called by every thread of the CTA; contains two __syncthreads.
+// One tile.  in: the raw tile as loaded (NOT offset-subtracted), chunk element e at in[10 + e],
+// halo at in[1..9]; pad: X's copy (subtracted), element e at pad[e + 2 (e / 48)], halo element -k
+// at pad[-2 - k].  Returns the thread's sums of squared differences in v[0..3]; no barrier inside.
+// SUB: subtract the tile offset (the first element of the tile) from every sample before it is
+// used.  It cancels in every difference; removing it keeps the rounding of the cluster sums at
+// the level of the signal's VARIATION instead of its magnitude, which matters for the decade sums
+// of the upper levels (magnitude ~ 10^k, variation ~ 10^(k/2)).  Level 0 adds at most 10 raw
+// samples per cluster and skips it (off = 0 there, and X's copy is made unsubtracted).
+template <bool SUB>
 __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, int64_t series, int64_t chunk,
-                                                   const double* x, const double* pad, double off10,
-                                                   AllanTileSmem& sm) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int kW1 = kAllanWarpsA1, kW2 = kW1 + kAllanWarpsA2, kW3 = kW2 + kAllanWarpsC1;
-  const int role = (warp >= kW1) + (warp >= kW2) + (warp >= kW3);
-  const int item = tid - 32 * (role == 0 ? 0 : role == 1 ? kW1 : role == 2 ? kW2 : kW3);
-  const bool has_prev = chunk != 0;
-  double v0 = 0.0, v1 = 0.0, v2 = 0.0;   // the role's sums of squared differences
-  double f0 = 0.0, f1 = 0.0, f2 = 0.0;   // first clusters of the item
+                                                   const double* in, const double* pad, double off,
+                                                   double (&v)[4]) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int kW1 = kAllanWarpsX, kW2 = kW1 + kAllanWarpsY;
+  const int role = (warp >= kW1) + (warp >= kW2);
+  const int item = tid - 32 * (role == 0 ? 0 : role == 1 ? kW1 : kW2);
+  const bool left = item > 0 || chunk != 0;   // the item has a left neighbour in this series
+  const double* x = in + kAllanLead;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;   // the role's sums of squared differences
   if (role == 0) {
-    if (item < kAllanItemsA1) {   // j = 2, 4, 8 in two blocks of 24 samples
+    if (item < kAllanItemsX) {   // j = 2, 4, 8: the 8 samples to the left, then two blocks of 24
       const double2* src = reinterpret_cast<const double2*>(pad + 50 * item);
-      double pP = 0.0, pQ = 0.0, pO = 0.0;
+      double pP, pQ, pO;
+      {
+        const double2 t0 = src[-5], t1 = src[-4], t2 = src[-3], t3 = src[-2];
+        pP = t3.x + t3.y;
+        pQ = (t2.x + t2.y) + pP;
+        pO = ((t0.x + t0.y) + (t1.x + t1.y)) + pQ;
+      }
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
         double P[12], Q[6], O[3];
@@ -234,25 +257,34 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
         for (int i = 0; i < 6; ++i) Q[i] = P[2 * i] + P[2 * i + 1];
 #pragma unroll
         for (int i = 0; i < 3; ++i) O[i] = Q[2 * i] + Q[2 * i + 1];
-        if (sb == 0) {
-          f0 = P[0]; f1 = Q[0]; f2 = O[0];
-        } else {
+        if (sb > 0 || left) {
           v0 = sq_acc(P[0], pP, v0); v1 = sq_acc(Q[0], pQ, v1); v2 = sq_acc(O[0], pO, v2);
         }
         v0 += sum_sq_diff(P); v1 += sum_sq_diff(Q); v2 += sum_sq_diff(O);
         pP = P[11]; pQ = Q[5]; pO = O[2];
       }
-      sm.last_a1[item][0] = pP; sm.last_a1[item][1] = pQ; sm.last_a1[item][2] = pO;
     }
   } else if (role == 1) {
-    if (item < kAllanItemsA2) {   // j = 3, 6, 9 on 18 samples
-      const double2* src = reinterpret_cast<const double2*>(x + 18 * item);
+    if (item < kAllanItemsY) {   // j = 1, 3, 6, 9: the 9 samples to the left, then 18 samples
+      const double* xs = x + 18 * item;
+      const double2* src = reinterpret_cast<const double2*>(xs);
       double y[18], T[6], S[3], N[2];
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         const double2 t = src[i];
-        y[2 * i] = t.x;
-        y[2 * i + 1] = t.y;
+        y[2 * i] = SUB ? t.x - off : t.x;
+        y[2 * i + 1] = SUB ? t.y - off : t.y;
+      }
+      double py, pT, pS, pN;
+      {
+        double l[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) l[k] = SUB ? xs[k - 9] - off : xs[k - 9];
+        py = l[8];
+        pT = (l[6] + l[7]) + l[8];
+        const double t1 = (l[3] + l[4]) + l[5], t0 = (l[0] + l[1]) + l[2];
+        pS = t1 + pT;
+        pN = (t0 + t1) + pT;
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) T[i] = (y[3 * i] + y[3 * i + 1]) + y[3 * i + 2];
@@ -260,124 +292,92 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
       for (int i = 0; i < 3; ++i) S[i] = T[2 * i] + T[2 * i + 1];
 #pragma unroll
       for (int i = 0; i < 2; ++i) N[i] = (T[3 * i] + T[3 * i + 1]) + T[3 * i + 2];
-      f0 = T[0]; f1 = S[0]; f2 = N[0];
-      v0 = sum_sq_diff(T); v1 = sum_sq_diff(S); v2 = sum_sq_diff(N);
-      sm.last_a2[item][0] = T[5]; sm.last_a2[item][1] = S[2]; sm.last_a2[item][2] = N[1];
-    }
-  } else if (role == 2) {
-    if (item < kAllanItemsC1) {   // j = 1, 7 in three blocks of 14 samples
-      const double2* src = reinterpret_cast<const double2*>(x + 42 * item);
-      double py = 0.0, pG = 0.0;
-      // j = 1: the left neighbour of the item's first sample is in the raw tile (halo for item 0)
-      const bool left = item > 0 || has_prev;
-      if (left) py = x[42 * item - 1];
-#pragma unroll
-      for (int sb = 0; sb < 3; ++sb) {
-        double y[14], G[2];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          const double2 t = src[7 * sb + i];
-          y[2 * i] = t.x;
-          y[2 * i + 1] = t.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          G[i] = ((y[7 * i] + y[7 * i + 1]) + (y[7 * i + 2] + y[7 * i + 3])) + ((y[7 * i + 4] + y[7 * i + 5]) + y[7 * i + 6]);
-        if (sb == 0) {
-          f1 = G[0];
-          if (left) v0 = sq_acc(y[0], py, v0);
-        } else {
-          v0 = sq_acc(y[0], py, v0);
-          v1 = sq_acc(G[0], pG, v1);
-        }
-        v0 += sum_sq_diff(y);
-        v1 = sq_acc(G[1], G[0], v1);
-        py = y[13]; pG = G[1];
+      v0 = sum_sq_diff(T); v1 = sum_sq_diff(S); v2 = sum_sq_diff(N); v3 = sum_sq_diff(y);
+      if (left) {
+        v0 = sq_acc(T[0], pT, v0); v1 = sq_acc(S[0], pS, v1); v2 = sq_acc(N[0], pN, v2);
+        v3 = sq_acc(y[0], py, v3);
       }
-      sm.last_c1[item] = pG;
     }
   } else {
-    if (item < kAllanItemsC2) {   // j = 5 and the decade sums, in three blocks of 10 samples
-      const double2* src = reinterpret_cast<const double2*>(x + 30 * item);
-      double* nx = p.next + series * p.next_pitch + (chunk * kAllanChunk) / 10 + 3 * item;
-      double pF = 0.0;
+    if (item < kAllanItemsC) {   // j = 5, 7 and the decade sums: the 7 samples to the left, then 70
+      const double* xs = x + 70 * item;
+      const double2* src = reinterpret_cast<const double2*>(xs);
+      double* nx = p.next + series * p.next_pitch + (chunk * kAllanChunk) / 10 + 7 * item;
+      const double off10 = SUB ? 10.0 * off : 0.0;
+      double pF, pG;
+      {
+        double l[7];
 #pragma unroll
-      for (int sb = 0; sb < 3; ++sb) {
+        for (int k = 0; k < 7; ++k) l[k] = SUB ? xs[k - 7] - off : xs[k - 7];
+        pF = ((l[2] + l[3]) + (l[4] + l[5])) + l[6];
+        pG = ((l[0] + l[1]) + (l[2] + l[3])) + ((l[4] + l[5]) + l[6]);
+      }
+      // the 70 samples stream through in blocks of 10 (fives, decades); the sevens are gathered
+      // from a 14-sample window that slides over the blocks (all indices are compile-time)
+      double w[14];   // samples 14 g .. 14 g + 13 of the current seven-pair g
+#pragma unroll
+      for (int sb = 0; sb < 7; ++sb) {
         double y[10];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
           const double2 t = src[5 * sb + i];
-          y[2 * i] = t.x;
-          y[2 * i + 1] = t.y;
+          y[2 * i] = SUB ? t.x - off : t.x;
+          y[2 * i + 1] = SUB ? t.y - off : t.y;
         }
         const double F0 = ((y[0] + y[1]) + (y[2] + y[3])) + y[4];
         const double F1 = ((y[5] + y[6]) + (y[7] + y[8])) + y[9];
-        if (sb == 0) f0 = F0; else v0 = sq_acc(F0, pF, v0);
+        if (sb > 0 || left) v0 = sq_acc(F0, pF, v0);
         v0 = sq_acc(F1, F0, v0);
         pF = F1;
         if (p.next_len > 0) nx[sb] = (F0 + F1) + off10;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int e = 10 * sb + i;      // sample index in the item
+          w[e % 14] = y[i];
+          if (e % 14 == 13) {             // a pair of sevens is complete
+            const double G0 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + w[6]);
+            const double G1 = ((w[7] + w[8]) + (w[9] + w[10])) + ((w[11] + w[12]) + w[13]);
+            if (e > 13 || left) v1 = sq_acc(G0, pG, v1);
+            v1 = sq_acc(G1, G0, v1);
+            pG = G1;
+          }
+        }
       }
-      sm.last_c2[item] = pF;
     }
   }
-  __syncthreads();
-  // the difference across the left edge of every item: neighbour's last clusters, halo for item 0
-  if (role == 0) {
-    if (item > 0 && item < kAllanItemsA1) {
-      const double* l = sm.last_a1[item - 1];
-      v0 = sq_acc(f0, l[0], v0); v1 = sq_acc(f1, l[1], v1); v2 = sq_acc(f2, l[2], v2);
-    } else if (item == 0 && has_prev) {
-      const double pp3 = x[-2] + x[-1], pp2 = x[-4] + x[-3], pp1 = x[-6] + x[-5], pp0 = x[-8] + x[-7];
-      v0 = sq_acc(f0, pp3, v0);
-      v1 = sq_acc(f1, pp2 + pp3, v1);
-      v2 = sq_acc(f2, (pp0 + pp1) + (pp2 + pp3), v2);
-    }
-  } else if (role == 1) {
-    if (item > 0 && item < kAllanItemsA2) {
-      const double* l = sm.last_a2[item - 1];
-      v0 = sq_acc(f0, l[0], v0); v1 = sq_acc(f1, l[1], v1); v2 = sq_acc(f2, l[2], v2);
-    } else if (item == 0 && has_prev) {
-      const double u2 = (x[-3] + x[-2]) + x[-1], u1 = (x[-6] + x[-5]) + x[-4], u0 = (x[-9] + x[-8]) + x[-7];
-      v0 = sq_acc(f0, u2, v0);
-      v1 = sq_acc(f1, u1 + u2, v1);
-      v2 = sq_acc(f2, (u0 + u1) + u2, v2);
-    }
-  } else if (role == 2) {
-    if (item > 0 && item < kAllanItemsC1) {
-      v1 = sq_acc(f1, sm.last_c1[item - 1], v1);
-    } else if (item == 0 && has_prev) {
-      v1 = sq_acc(f1, ((x[-7] + x[-6]) + (x[-5] + x[-4])) + ((x[-3] + x[-2]) + x[-1]), v1);
-    }
-  } else {
-    if (item > 0 && item < kAllanItemsC2) {
-      v0 = sq_acc(f0, sm.last_c2[item - 1], v0);
-    } else if (item == 0 && has_prev) {
-      v0 = sq_acc(f0, ((x[-5] + x[-4]) + (x[-3] + x[-2])) + x[-1], v0);
-    }
-  }
-  // ---- block reduction: one packed butterfly per warp, then the role's warps in order ------------
-  const double t = warp_sum4(v0, v1, v2, 0.0, lane);
-  if ((lane & 7) == 0) sm.red[warp][lane >> 3] = t;
-  __syncthreads();
-  if (tid < 9) {
-    // j = tid + 1 is held by role {2,0,1,0,3,1,2,0,1}[tid] in column {0,0,0,1,0,1,1,2,2}[tid]
-    const int r = static_cast<int>((0x102130102ull >> (4 * tid)) & 15);
-    const int c = static_cast<int>((0x221101000ull >> (4 * tid)) & 15);
-    const int w0 = r == 0 ? 0 : r == 1 ? kW1 : r == 2 ? kW2 : kW3;
-    const int w1 = r == 0 ? kW1 : r == 1 ? kW2 : r == 2 ? kW3 : kAllanFastWarps;
-    double v = 0.0;
-    for (int w = w0; w < w1; ++w) v += sm.red[w][c];
-    p.partial[(series * p.chunks + chunk) * 9 + tid] = (tid < p.jmax) ? v : 0.0;
-  }
+  v[0] = v0; v[1] = v1; v[2] = v2; v[3] = v3;
+}
+
+// one packed butterfly per warp; allan_tile_fold adds the role's warps in order after a barrier
+__device__ __forceinline__ void allan_tile_reduce(const double (&v)[4], double (*red)[4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double t = warp_sum4(v[0], v[1], v[2], v[3], lane);
+  if ((lane & 7) == 0) red[warp][lane >> 3] = t;
+}
+
+// threads 0..8, after a barrier behind allan_tile_compute: partial sums of the chunk for j = tid+1
+__device__ __forceinline__ void allan_tile_fold(const AllanLevelParams& p, int64_t series, int64_t chunk,
+                                                const double (*red)[4]) {
+  const int tid = threadIdx.x;
+  constexpr int kW1 = kAllanWarpsX, kW2 = kW1 + kAllanWarpsY;
+  // j = tid + 1 is held by role {1,0,1,0,2,1,2,0,1}[tid] in column {3,0,0,1,0,1,1,2,2}[tid]
+  const int r = static_cast<int>((0x102120101ull >> (4 * tid)) & 15);
+  const int c = static_cast<int>((0x221101003ull >> (4 * tid)) & 15);
+  const int w0 = r == 0 ? 0 : r == 1 ? kW1 : kW2;
+  const int w1 = r == 0 ? kW1 : r == 1 ? kW2 : kAllanFastWarps;
+  double v = 0.0;
+#pragma unroll
+  for (int w = 0; w < kAllanWarpsY; ++w)
+    if (w0 + w < w1) v += red[w0 + w][c];
+  p.partial[(series * p.chunks + chunk) * 9 + tid] = (tid < p.jmax) ? v : 0.0;
 }
 
 template <bool UNIT>   // UNIT: consecutive samples are adjacent in memory
-__global__ void __launch_bounds__(kAllanFastThreads, 1) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
+__global__ void __launch_bounds__(kAllanFastThreads, 2) allan_full_kernel(const __grid_constant__ AllanLevelParams p) {
   extern __shared__ __align__(128) double smem[];
-  double* raw = smem;                                  // [kAllanRawLen]
-  double* pad48 = smem + kAllanRawLen;                 // [kAllanPad48]: element e at e + 2*(e/48)
-  __shared__ AllanTileSmem sm;
-  __shared__ double sh_off10;
+  double* in = smem;                                   // [kAllanRawLen] raw tile, as loaded
+  double* pad = smem + kAllanRawLen + kAllanPadLead;   // X's padded, offset-subtracted copy
+  __shared__ double red[kAllanFastWarps][4];
   const int64_t series = blockIdx.x / p.chunk_count;
   const int64_t chunk = p.chunk_first + blockIdx.x % p.chunk_count;
   const int64_t c0 = chunk * kAllanChunk;
@@ -392,109 +392,134 @@ __global__ void __launch_bounds__(kAllanFastThreads, 1) allan_full_kernel(const 
     base = p.src + series * p.src_pitch;
     stride = 1;
   }
-  double* x = raw + kAllanLead;                        // x[e], e in [-9, kAllanChunk); 16-B aligned
+  const double off = p.level0 ? 0.0 : base[(c0 - (has_prev ? kAllanHalo : 0)) * stride];
   {
-    // loaders: thread (g, pos) loads element 48 (15 q + g) + pos in pass q; every load is issued
-    // before the first use (7 independent requests in flight per thread)
-    constexpr int kLoaders = 720;   // 15 blocks of 48 per pass, 7 passes
+    // loaders: thread (g, pos) loads element 48 (7 q + g) + pos in pass q; every load is issued
+    // before the first use (15 independent requests in flight per thread)
+    constexpr int kLoaders = 336;   // 7 blocks of 48 per pass, 15 passes
+    constexpr int kPasses = 15;
     const int g = tid / 48, pos = tid - 48 * g;
     const double* src = base + (c0 + 48 * g + pos) * stride;
-    const double off = base[(c0 - (has_prev ? kAllanHalo : 0)) * stride];
-    double v[7];
+    double v[kPasses];
     double hv = 0.0;
     if (tid < kLoaders) {
 #pragma unroll
-      for (int q = 0; q < 7; ++q) v[q] = src[static_cast<int64_t>(q) * kLoaders * stride];
+      for (int q = 0; q < kPasses; ++q) v[q] = src[static_cast<int64_t>(q) * kLoaders * stride];
     } else if (has_prev && tid < kLoaders + kAllanHalo) {
       hv = base[(c0 - kAllanHalo + (tid - kLoaders)) * stride];
     }
     if (tid < kLoaders) {
-      double* xr = x + 48 * g + pos;
-      double* xp = pad48 + 50 * g + pos;
+      double* xr = in + kAllanLead + 48 * g + pos;
+      double* xp = pad + 50 * g + pos;
 #pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const double w = v[q] - off;
-        xr[q * kLoaders] = w;
-        xp[q * 15 * 50] = w;
+      for (int q = 0; q < kPasses; ++q) {
+        xr[q * kLoaders] = v[q];
+        xp[q * 7 * 50] = v[q] - off;   // off = 0 at level 0
       }
-    } else if (has_prev && tid < kLoaders + kAllanHalo) {
-      x[tid - kLoaders - kAllanHalo] = hv - off;
+    } else if (tid < kLoaders + kAllanHalo) {
+      const int k = kAllanHalo - (tid - kLoaders);   // halo element -k, k = 9..1
+      in[kAllanLead - k] = hv;                       // zeros without a left neighbour (unused)
+      pad[-2 - k] = hv - off;
     }
-    if (tid == 0) sh_off10 = 10.0 * off;   // decade sums carry the offset back
   }
   __syncthreads();
-  allan_tile_compute(p, series, chunk, x, pad48, sh_off10, sm);
+  double acc[4];
+  if (p.level0)
+    allan_tile_compute<false>(p, series, chunk, in, pad, 0.0, acc);
+  else
+    allan_tile_compute<true>(p, series, chunk, in, pad, off, acc);
+  allan_tile_reduce(acc, red);
+  __syncthreads();
+  if (tid < 9) allan_tile_fold(p, series, chunk, red);
 }
 
-// Persistent front end: CTA b takes tiles b, b + grid, ...; the raw tile (with its halo) arrives
-// by one bulk copy into a two-stage ring, is offset-subtracted into the two working copies by all
-// threads, and the stage is handed back to the copy engine for the tile after the next before the
-// cluster sums are computed -- two tiles are always in flight per SM.
-constexpr int kAllanStages = 2;
+// Persistent front end: CTA b takes tiles b, b + grid, ...
+constexpr int kAllanStages = 3;
+template <bool SUB>
 __global__ void __launch_bounds__(kAllanFastThreads, 1) allan_stream_kernel(const __grid_constant__ AllanLevelParams p) {
   extern __shared__ __align__(128) double smem[];
   double* in_buf = smem;                                          // [kAllanStages][kAllanRawLen]
-  double* raw = smem + kAllanStages * kAllanRawLen;               // [kAllanRawLen]
-  double* pad48 = raw + kAllanRawLen;                             // [kAllanPad48]
-  __shared__ AllanTileSmem sm;
+  double* pad_buf = smem + kAllanStages * kAllanRawLen;           // [2][kAllanPadLen]
+  __shared__ double red[2][kAllanFastWarps][4];
   __shared__ __align__(8) uint64_t full[kAllanStages];
   const int tid = threadIdx.x;
-  const int64_t tiles = p.nseries * p.chunk_count;
-  auto issue = [&](int64_t tile, int stage) {
-    const int64_t series = tile / p.chunk_count, chunk = tile % p.chunk_count;
+  const int tiles = static_cast<int>(p.nseries * p.chunk_count);   // < 2^31 (checked by the host)
+  const int cc = static_cast<int>(p.chunk_count);
+  auto issue = [&](int series, int chunk, int slot) {
     const double* base = p.level0 ? p.src + series * p.outer_stride : p.src + series * p.src_pitch;
     const int lead = (chunk != 0) ? kAllanLead : 0;
     const uint32_t bytes = static_cast<uint32_t>((kAllanChunk + lead) * sizeof(double));
-    mbar_arrive_expect_tx(&full[stage], bytes);
-    bulk_g2s(in_buf + stage * kAllanRawLen + (kAllanLead - lead), base + chunk * kAllanChunk - lead, bytes,
-             &full[stage]);
+    mbar_arrive_expect_tx(&full[slot], bytes);
+    bulk_g2s(in_buf + slot * kAllanRawLen + (kAllanLead - lead),
+             base + static_cast<int64_t>(chunk) * kAllanChunk - lead, bytes, &full[slot]);
   };
+  // (series, chunk) of this CTA's tiles, advanced by gridDim.x tiles at a time without divisions
+  const int step_s = static_cast<int>(gridDim.x) / cc, step_c = static_cast<int>(gridDim.x) % cc;
+  auto advance = [&](int& series, int& chunk) {
+    series += step_s;
+    chunk += step_c;
+    if (chunk >= cc) {
+      chunk -= cc;
+      ++series;
+    }
+  };
+  int series = static_cast<int>(blockIdx.x) / cc, chunk = static_cast<int>(blockIdx.x) % cc;
+  int fs = series, fc = chunk;   // the tile two ahead (the one to fetch)
   if (tid == 0) {
     for (int s = 0; s < kAllanStages; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
-    for (int s = 0; s < kAllanStages; ++s) {
-      const int64_t tile = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
-      if (tile < tiles) issue(tile, s);
+    int tile = blockIdx.x;
+    for (int s = 0; s < 2; ++s) {
+      if (tile < tiles) issue(fs, fc, s);
+      advance(fs, fc);
+      tile += gridDim.x;
     }
   }
   __syncthreads();
   int it = 0;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-    const int stage = it % kAllanStages;
-    const int64_t series = tile / p.chunk_count, chunk = tile % p.chunk_count;
-    const bool has_prev = chunk != 0;
-    mbar_wait(&full[stage], (it / kAllanStages) & 1);
-    const double* in = in_buf + stage * kAllanRawLen;
-    const double off = in[has_prev ? 1 : kAllanLead];
+  int prev_series = 0, prev_chunk = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int slot = it % kAllanStages;
+    mbar_wait(&full[slot], (it / kAllanStages) & 1);
+    const double* in = in_buf + slot * kAllanRawLen;
+    double* pad = pad_buf + (it & 1) * kAllanPadLen + kAllanPadLead;
+    const double off = SUB ? in[chunk != 0 ? 1 : kAllanLead] : 0.0;
     {
+      // X's copy: units of two samples; the five halo units land just below pad[0]
       const double2* in2 = reinterpret_cast<const double2*>(in);
-      double2* raw2 = reinterpret_cast<double2*>(raw);
-      double2* pad2 = reinterpret_cast<double2*>(pad48);
+      double2* pad2 = reinterpret_cast<double2*>(pad);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 5; ++q) {
         const int u = tid + q * kAllanFastThreads;
         if (u < (kAllanLead + kAllanChunk) / 2) {
           double2 w = in2[u];
-          w.x -= off;
-          w.y -= off;
-          raw2[u] = w;
+          if (SUB) {
+            w.x -= off;
+            w.y -= off;
+          }
           const int ue = u - kAllanLead / 2;
-          if (ue >= 0) pad2[ue + ue / 24] = w;
+          pad2[ue >= 0 ? ue + ue / 24 : ue - 1] = w;
         }
       }
     }
-    __syncthreads();   // both copies complete; the stage has been consumed
-    if (tid == 0) {
-      const int64_t nxt = tile + static_cast<int64_t>(kAllanStages) * gridDim.x;
-      if (nxt < tiles) {
+    __syncthreads();   // the only barrier of the tile: pad complete; everybody has finished tile it-1
+    if (tid == 0) {    // the slot of tile it-1 is free: fetch tile it+2 into it
+      if (tile + 2 * static_cast<int>(gridDim.x) < tiles) {
         fence_async_smem();
-        issue(nxt, stage);
+        issue(fs, fc, (it + 2) % kAllanStages);
       }
+      advance(fs, fc);
     }
-    allan_tile_compute(p, series, chunk, raw + kAllanLead, pad48, 10.0 * off, sm);
-    // the next pass overwrites raw / pad48: every read of them precedes the last barrier inside
-    // allan_tile_compute; sm.red is rewritten only after two more barriers
+    if (it > 0 && tid < 9) allan_tile_fold(p, prev_series, prev_chunk, red[(it - 1) & 1]);
+    double acc[4];
+    allan_tile_compute<SUB>(p, series, chunk, in, pad, off, acc);
+    allan_tile_reduce(acc, red[it & 1]);
+    prev_series = series;
+    prev_chunk = chunk;
+    advance(series, chunk);
   }
+  __syncthreads();
+  if (it > 0 && tid < 9) allan_tile_fold(p, prev_series, prev_chunk, red[(it - 1) & 1]);
 }
 
 struct AllanFinalParams {
@@ -564,7 +589,18 @@ __global__ void __launch_bounds__(kAllanRestThreads) allan_rest_kernel(const __g
       base = p.src + series * p.src_pitch;
       stride = 1;
     }
-    for (int e = tid; e < len; e += kAllanRestThreads) buf_a[e] = base[e * stride];
+    constexpr int kPer = (kAllanChunk + kAllanRestThreads - 1) / kAllanRestThreads;
+    double v[kPer];   // every load is issued before the first store
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int e = tid + q * kAllanRestThreads;
+      v[q] = (e < len) ? base[e * stride] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int e = tid + q * kAllanRestThreads;
+      if (e < len) buf_a[e] = v[q];
+    }
   }
   __syncthreads();
   for (int k = 0; k < p.levels; ++k) {
@@ -666,8 +702,8 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
   double* part = ws + 2 * n1 * nseries;
   int64_t len = n;
   const size_t smem = (kAllanChunk + kAllanHalo + 1 + 16) * sizeof(double);
-  const size_t smem_full = (kAllanRawLen + kAllanPad48) * sizeof(double);
-  const size_t smem_stream = ((kAllanStages + 1) * kAllanRawLen + kAllanPad48) * sizeof(double);
+  const size_t smem_full = (kAllanRawLen + kAllanPadLen) * sizeof(double);
+  const size_t smem_stream = (kAllanStages * kAllanRawLen + 2 * kAllanPadLen) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(allan_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -677,7 +713,9 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
                              static_cast<int>(smem_full)) != cudaSuccess ||
         cudaFuncSetAttribute(allan_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem_full)) != cudaSuccess ||
-        cudaFuncSetAttribute(allan_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(allan_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_stream)) != cudaSuccess ||
+        cudaFuncSetAttribute(allan_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem_stream)) != cudaSuccess)
       return 2;
     // both kernels stage everything through shared memory: ask for the largest carve-out so that
@@ -744,7 +782,10 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
                                           (outer_stride & 1) == 0);
       if (contiguous && aligned) {
         const int64_t grid = tiles < sms ? tiles : sms;
-        allan_stream_kernel<<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
+        if (lp.level0)
+          allan_stream_kernel<false><<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
+        else
+          allan_stream_kernel<true><<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
       } else if (contiguous) {
         allan_full_kernel<true><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
       } else {
