@@ -202,6 +202,27 @@ __device__ __forceinline__ double sum_sq_diff(const double (&c)[N]) {
   return (a[0] + a[1]) + (a[2] + a[3]);
 }
 
+// The same with a validity mask for the ragged last chunk of a series: cluster i ends (exclusive)
+// at local element end0 + i * step and counts only if that is within lim (the elements of the
+// chunk covered by COMPLETE clusters of this size).  Selects, not multiplications: what lies
+// beyond the end of the series in shared memory is stale data.
+template <int N, bool RAGGED>
+__device__ __forceinline__ double sum_sq_diff_m(const double (&c)[N], int end0, int step, int lim) {
+  if (!RAGGED) return sum_sq_diff(c);
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 1; i < N; ++i) {
+    const double t = sq_acc(c[i], c[i - 1], a[i & 3]);
+    a[i & 3] = (end0 + i * step <= lim) ? t : a[i & 3];
+  }
+  return (a[0] + a[1]) + (a[2] + a[3]);
+}
+template <bool RAGGED>
+__device__ __forceinline__ double sq_acc_m(double a, double b, double acc, int end, int lim) {
+  const double t = sq_acc(a, b, acc);
+  return (!RAGGED || end <= lim) ? t : acc;
+}
+
 // Warp totals of four values per lane in 5 packed butterfly steps; lane L returns the total of
 // value number L >> 3.  Fixed pairing: deterministic.
 __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, int lane) {
@@ -224,7 +245,9 @@ __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, dou
 // the level of the signal's VARIATION instead of its magnitude, which matters for the decade sums
 // of the upper levels (magnitude ~ 10^k, variation ~ 10^(k/2)).  Level 0 adds at most 10 raw
 // samples per cluster and skips it (off = 0 there, and X's copy is made unsubtracted).
-template <bool SUB>
+// RAGGED: the last chunk of a series (fewer than 5040 elements): every term is masked by the
+// number of elements its cluster size covers with complete clusters.
+template <bool SUB, bool RAGGED>
 __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, int64_t series, int64_t chunk,
                                                    const double* in, const double* pad, double off,
                                                    double (&v)[4]) {
@@ -234,10 +257,14 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
   const int item = tid - 32 * (role == 0 ? 0 : role == 1 ? kW1 : kW2);
   const bool left = item > 0 || chunk != 0;   // the item has a left neighbour in this series
   const double* x = in + kAllanLead;
+  // elements of this chunk covered by complete clusters of size j (only used when RAGGED)
+  const int64_t c0 = chunk * kAllanChunk;
+  auto lim = [&](int j) { return RAGGED ? static_cast<int>((p.len / j) * j - c0) : kAllanChunk; };
   double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;   // the role's sums of squared differences
   if (role == 0) {
     if (item < kAllanItemsX) {   // j = 2, 4, 8: the 8 samples to the left, then two blocks of 24
       const double2* src = reinterpret_cast<const double2*>(pad + 50 * item);
+      const int l2 = lim(2), l4 = lim(4), l8 = lim(8);
       double pP, pQ, pO;
       {
         const double2 t0 = src[-5], t1 = src[-4], t2 = src[-3], t3 = src[-2];
@@ -257,10 +284,15 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
         for (int i = 0; i < 6; ++i) Q[i] = P[2 * i] + P[2 * i + 1];
 #pragma unroll
         for (int i = 0; i < 3; ++i) O[i] = Q[2 * i] + Q[2 * i + 1];
+        const int eb = 48 * item + 24 * sb;
         if (sb > 0 || left) {
-          v0 = sq_acc(P[0], pP, v0); v1 = sq_acc(Q[0], pQ, v1); v2 = sq_acc(O[0], pO, v2);
+          v0 = sq_acc_m<RAGGED>(P[0], pP, v0, eb + 2, l2);
+          v1 = sq_acc_m<RAGGED>(Q[0], pQ, v1, eb + 4, l4);
+          v2 = sq_acc_m<RAGGED>(O[0], pO, v2, eb + 8, l8);
         }
-        v0 += sum_sq_diff(P); v1 += sum_sq_diff(Q); v2 += sum_sq_diff(O);
+        v0 += sum_sq_diff_m<12, RAGGED>(P, eb + 2, 2, l2);
+        v1 += sum_sq_diff_m<6, RAGGED>(Q, eb + 4, 4, l4);
+        v2 += sum_sq_diff_m<3, RAGGED>(O, eb + 8, 8, l8);
         pP = P[11]; pQ = Q[5]; pO = O[2];
       }
     }
@@ -292,10 +324,17 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
       for (int i = 0; i < 3; ++i) S[i] = T[2 * i] + T[2 * i + 1];
 #pragma unroll
       for (int i = 0; i < 2; ++i) N[i] = (T[3 * i] + T[3 * i + 1]) + T[3 * i + 2];
-      v0 = sum_sq_diff(T); v1 = sum_sq_diff(S); v2 = sum_sq_diff(N); v3 = sum_sq_diff(y);
+      const int e0 = 18 * item;
+      const int l1 = lim(1), l3 = lim(3), l6 = lim(6), l9 = lim(9);
+      v0 = sum_sq_diff_m<6, RAGGED>(T, e0 + 3, 3, l3);
+      v1 = sum_sq_diff_m<3, RAGGED>(S, e0 + 6, 6, l6);
+      v2 = sum_sq_diff_m<2, RAGGED>(N, e0 + 9, 9, l9);
+      v3 = sum_sq_diff_m<18, RAGGED>(y, e0 + 1, 1, l1);
       if (left) {
-        v0 = sq_acc(T[0], pT, v0); v1 = sq_acc(S[0], pS, v1); v2 = sq_acc(N[0], pN, v2);
-        v3 = sq_acc(y[0], py, v3);
+        v0 = sq_acc_m<RAGGED>(T[0], pT, v0, e0 + 3, l3);
+        v1 = sq_acc_m<RAGGED>(S[0], pS, v1, e0 + 6, l6);
+        v2 = sq_acc_m<RAGGED>(N[0], pN, v2, e0 + 9, l9);
+        v3 = sq_acc_m<RAGGED>(y[0], py, v3, e0 + 1, l1);
       }
     }
   } else {
@@ -304,6 +343,7 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
       const double2* src = reinterpret_cast<const double2*>(xs);
       double* nx = p.next + series * p.next_pitch + (chunk * kAllanChunk) / 10 + 7 * item;
       const double off10 = SUB ? 10.0 * off : 0.0;
+      const int l5 = lim(5), l7 = lim(7), l10 = lim(10);
       double pF, pG;
       {
         double l[7];
@@ -326,10 +366,11 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
         }
         const double F0 = ((y[0] + y[1]) + (y[2] + y[3])) + y[4];
         const double F1 = ((y[5] + y[6]) + (y[7] + y[8])) + y[9];
-        if (sb > 0 || left) v0 = sq_acc(F0, pF, v0);
-        v0 = sq_acc(F1, F0, v0);
+        const int eb = 70 * item + 10 * sb;
+        if (sb > 0 || left) v0 = sq_acc_m<RAGGED>(F0, pF, v0, eb + 5, l5);
+        v0 = sq_acc_m<RAGGED>(F1, F0, v0, eb + 10, l5);
         pF = F1;
-        if (p.next_len > 0) nx[sb] = (F0 + F1) + off10;
+        if (p.next_len > 0 && (!RAGGED || eb + 10 <= l10)) nx[sb] = (F0 + F1) + off10;
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
           const int e = 10 * sb + i;      // sample index in the item
@@ -337,8 +378,8 @@ __device__ __forceinline__ void allan_tile_compute(const AllanLevelParams& p, in
           if (e % 14 == 13) {             // a pair of sevens is complete
             const double G0 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + w[6]);
             const double G1 = ((w[7] + w[8]) + (w[9] + w[10])) + ((w[11] + w[12]) + w[13]);
-            if (e > 13 || left) v1 = sq_acc(G0, pG, v1);
-            v1 = sq_acc(G1, G0, v1);
+            if (e > 13 || left) v1 = sq_acc_m<RAGGED>(G0, pG, v1, 70 * item + e - 6, l7);
+            v1 = sq_acc_m<RAGGED>(G1, G0, v1, 70 * item + e + 1, l7);
             pG = G1;
           }
         }
@@ -425,9 +466,9 @@ __global__ void __launch_bounds__(kAllanFastThreads, 2) allan_full_kernel(const 
   __syncthreads();
   double acc[4];
   if (p.level0)
-    allan_tile_compute<false>(p, series, chunk, in, pad, 0.0, acc);
+    allan_tile_compute<false, false>(p, series, chunk, in, pad, 0.0, acc);
   else
-    allan_tile_compute<true>(p, series, chunk, in, pad, off, acc);
+    allan_tile_compute<true, false>(p, series, chunk, in, pad, off, acc);
   allan_tile_reduce(acc, red);
   __syncthreads();
   if (tid < 9) allan_tile_fold(p, series, chunk, red);
@@ -448,10 +489,15 @@ __global__ void __launch_bounds__(kAllanFastThreads, 1) allan_stream_kernel(cons
   auto issue = [&](int series, int chunk, int slot) {
     const double* base = p.level0 ? p.src + series * p.outer_stride : p.src + series * p.src_pitch;
     const int lead = (chunk != 0) ? kAllanLead : 0;
-    const uint32_t bytes = static_cast<uint32_t>((kAllanChunk + lead) * sizeof(double));
+    const int64_t c0 = static_cast<int64_t>(chunk) * kAllanChunk;
+    const int64_t left_in_series = p.len - c0;
+    const int cnt = left_in_series < kAllanChunk ? static_cast<int>(left_in_series) : kAllanChunk;
+    const int avail = cnt + lead;                      // elements to fetch
+    double* dst = in_buf + slot * kAllanRawLen + (kAllanLead - lead);
+    const uint32_t bytes = static_cast<uint32_t>((avail & ~1) * sizeof(double));
+    if (avail & 1) dst[avail - 1] = base[c0 - lead + avail - 1];   // a bulk copy moves whole 16 B
     mbar_arrive_expect_tx(&full[slot], bytes);
-    bulk_g2s(in_buf + slot * kAllanRawLen + (kAllanLead - lead),
-             base + static_cast<int64_t>(chunk) * kAllanChunk - lead, bytes, &full[slot]);
+    if (bytes) bulk_g2s(dst, base + c0 - lead, bytes, &full[slot]);
   };
   // (series, chunk) of this CTA's tiles, advanced by gridDim.x tiles at a time without divisions
   const int step_s = static_cast<int>(gridDim.x) / cc, step_c = static_cast<int>(gridDim.x) % cc;
@@ -512,7 +558,10 @@ __global__ void __launch_bounds__(kAllanFastThreads, 1) allan_stream_kernel(cons
     }
     if (it > 0 && tid < 9) allan_tile_fold(p, prev_series, prev_chunk, red[(it - 1) & 1]);
     double acc[4];
-    allan_tile_compute<SUB>(p, series, chunk, in, pad, off, acc);
+    if (static_cast<int64_t>(chunk + 1) * kAllanChunk <= p.len)
+      allan_tile_compute<SUB, false>(p, series, chunk, in, pad, off, acc);
+    else
+      allan_tile_compute<SUB, true>(p, series, chunk, in, pad, off, acc);
     allan_tile_reduce(acc, red[it & 1]);
     prev_series = series;
     prev_chunk = chunk;
@@ -769,33 +818,38 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
       allan_rest_kernel<<<static_cast<unsigned>(nseries), kAllanRestThreads, 0, s>>>(rp);
       break;
     }
-    // full chunks (every cluster complete, next-level decades complete) take the fast kernel
+    // full chunks (every cluster complete, next-level decades complete) take the fast kernels
     const int64_t full = len / kAllanChunk;
-    if (full > 0) {
+    const bool contiguous = !lp.level0 || sample_stride == 1;
+    // the bulk copies need 16-byte aligned rows: always true for the decade sums (even pitch),
+    // for the caller's series if the base and the row stride allow it
+    const bool aligned = !lp.level0 || (inner == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                                        (outer_stride & 1) == 0);
+    if (contiguous && aligned) {
+      // persistent kernel, every chunk of every series (the ragged last one is masked)
       lp.chunk_first = 0;
-      lp.chunk_count = full;
-      const int64_t tiles = full * nseries;
-      const bool contiguous = !lp.level0 || sample_stride == 1;
-      // the bulk copies need 16-byte aligned rows: always true for the decade sums (even pitch),
-      // for the caller's series if the base and the row stride allow it
-      const bool aligned = !lp.level0 || (inner == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                                          (outer_stride & 1) == 0);
-      if (contiguous && aligned) {
-        const int64_t grid = tiles < sms ? tiles : sms;
-        if (lp.level0)
-          allan_stream_kernel<false><<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
+      lp.chunk_count = lp.chunks;
+      const int64_t tiles = lp.chunks * nseries;
+      const int64_t grid = tiles < sms ? tiles : sms;
+      if (lp.level0)
+        allan_stream_kernel<false><<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
+      else
+        allan_stream_kernel<true><<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
+    } else {
+      if (full > 0) {
+        lp.chunk_first = 0;
+        lp.chunk_count = full;
+        const int64_t tiles = full * nseries;
+        if (contiguous)
+          allan_full_kernel<true><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
         else
-          allan_stream_kernel<true><<<static_cast<unsigned>(grid), kAllanFastThreads, smem_stream, s>>>(lp);
-      } else if (contiguous) {
-        allan_full_kernel<true><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
-      } else {
-        allan_full_kernel<false><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
+          allan_full_kernel<false><<<static_cast<unsigned>(tiles), kAllanFastThreads, smem_full, s>>>(lp);
       }
-    }
-    if (lp.chunks > full) {   // the ragged last chunk
-      lp.chunk_first = full;
-      lp.chunk_count = lp.chunks - full;
-      allan_level_kernel<<<static_cast<unsigned>(lp.chunk_count * nseries), kAllanThreads, smem, s>>>(lp);
+      if (lp.chunks > full) {   // the ragged last chunk
+        lp.chunk_first = full;
+        lp.chunk_count = lp.chunks - full;
+        allan_level_kernel<<<static_cast<unsigned>(lp.chunk_count * nseries), kAllanThreads, smem, s>>>(lp);
+      }
     }
     len /= 10;
   }

@@ -283,6 +283,22 @@ def test_k4_allan_interleaved_triads(eng):
     assert_close(tau.cpu().numpy(), t, 1e-15, 0.0, 'tau')
 
 
+@pytest.mark.parametrize('nser,n', [(1, 5041), (1, 5049), (1, 5050), (1, 10081), (1, 15129), (1, 10090),
+                                    (4, 10082), (4, 20170), (3, 5040), (2, 50400)])
+def test_k4_allan_ragged_last_chunk(eng, nser, n):
+    """The last chunk of a series holds 1 .. 5040 elements: every cluster size must count exactly
+    the clusters the reference counts (allan.py:44-57), whatever is left over."""
+    rng = np.random.RandomState(n)
+    fs = 100.0
+    x = 0.7 + rng.randn(nser, n) + np.cumsum(0.01 * rng.randn(nser, n), axis=1)
+    avar, tau = eng.allan(fs, _dev(x), n, nser)
+    avar = avar.cpu().numpy()
+    for r in range(nser):
+        o, t = onp.allan_var(x[r], fs)
+        assert_close(avar[r], o, 1e-9, 0.0, 'avar %d' % r)
+    assert_close(tau.cpu().numpy(), t, 1e-15, 0.0, 'tau')
+
+
 def test_host_entry_points(eng):
     """The *_host C-ABI calls (host buffers in, host buffers out)."""
     from gnss_ins_sim_b200 import _lib
