@@ -49,12 +49,12 @@ TRAJ = os.path.join(ROOT, 'tests', 'golden', 'traj_90deg_turn_100hz_rf1.npz')
 WORKLOAD = ("free_integration, motion_def-90deg_turn.csv (n=1000 @100Hz), 'mid-accuracy' IMU, "
             "ref_frame=1, 1000 MC runs per GPU")
 # FP64 thread-instructions (DFMA/DMUL/DADD/DSETP) one run-step costs in mc_kernel, by lane-group
-# width, from the ncu source-level counts in profiles/ncu_mc_kernel_r01_v3_*.json (lanes of a
+# width, from the ncu source-level counts in profiles/ncu_mc_kernel_r01_v5_*.json (lanes of a
 # group replicate the serial step, so wide groups spend more instructions per run-step)
-FP64_INST_PER_RUN_STEP = {16: 2145.6, 1: 648.0}
+FP64_INST_PER_RUN_STEP = {16: 1969.8, 1: 634.3}
 # dram__bytes_read.sum + dram__bytes_write.sum of one mc_kernel launch at this workload
-# (profiles/ncu_mc_kernel_r01_v3_cfg2_lanes16.json): the trajectory; the 72 KB of results stay in L2
-NCU_DRAM_BYTES_PER_LAUNCH = 129280
+# (profiles/ncu_mc_kernel_r01_v5_cfg2_lanes16.json): the trajectory; the 72 KB of results stay in L2
+NCU_DRAM_BYTES_PER_LAUNCH = 135680
 
 
 def load_workload():
@@ -309,7 +309,7 @@ def run_b200(args):
         fp64['frac'] = FP64_INST_PER_RUN_STEP[lanes_used] * k_rate / dfma.value
         fp64['frac_note'] = ('FP64 instructions issued / measured FP64-FMA issue rate; 1000 runs leave '
                              'the serial recurrence latency-bound (one warp per SM sub-partition); the '
-                             'same kernel reaches 0.56 at 10^6 runs (profiles/)')
+                             'same kernel reaches 0.59 at 10^6 runs (profiles/)')
 
     if args.quick:
         if rank == 0:

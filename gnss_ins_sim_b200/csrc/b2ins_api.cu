@@ -383,8 +383,22 @@ int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gy
     CU_CHECK(cudaMallocAsync(&scratch, sizeof(double) * runs * p.nseg * 12, s));
     p.seg_end = scratch;
     p.seg_carry = scratch + runs * p.nseg * 6;
+    // pass 1 only needs the drives that still matter at the segment end: a^L < 1e-20
+    int64_t keep = 1;
+    for (int c = 0; c < 6; ++c) {
+      const double a = (c < 3) ? p.accel.gm_a[c] : p.gyro.gm_a[c - 3];
+      if (a >= 1.0) {
+        keep = len;
+      } else if (a > 0.0) {
+        const double need = std::ceil(std::log(1e-20) / std::log(a));
+        if (need > static_cast<double>(keep)) keep = need >= static_cast<double>(len) ? len : static_cast<int64_t>(need);
+      }
+    }
+    keep = (keep + kNoiseThreads - 1) / kNoiseThreads * kNoiseThreads;
+    p.pass1_len = keep < len ? keep : len;
     p.pass = 1;
-    imu_noise_kernel<<<static_cast<unsigned>(runs * p.nseg), kNoiseThreads, 0, s>>>(p);
+    if (p.nseg > 1)
+      imu_noise_kernel<<<static_cast<unsigned>(runs * (p.nseg - 1)), kNoiseThreads, 0, s>>>(p);
     noise_carry_kernel<<<static_cast<unsigned>((runs * 6 + 127) / 128), 128, 0, s>>>(p);
     p.pass = 0;
   }

@@ -26,8 +26,12 @@ struct NoiseParams {
   // time segmentation (few runs, long series): blockIdx.x = run * nseg + seg, samples
   // [seg*seg_len, min(n, (seg+1)*seg_len)).  pass 0: write outputs, GM state at the segment
   // start taken from seg_carry[run][seg][6] (all zero for seg 0); pass 1: no output, only the
-  // zero-state GM response at the segment end -> seg_end[run][seg][6]
+  // zero-state GM response at the segment end -> seg_end[run][seg][6].  Pass 1 covers segments
+  // 0 .. nseg-2 only (the end value of the last one is never used: blockIdx.x = run * (nseg-1) +
+  // seg) and only their last pass1_len samples: older drives have decayed below 1e-20 of the
+  // state (pass1_len = seg_len if the correlation time is too long for that)
   int64_t seg_len;
+  int64_t pass1_len;
   int nseg;
   int pass;
   double* seg_carry;
@@ -60,10 +64,11 @@ __device__ __forceinline__ double gm_block_scan(double x, const double* apow, do
 __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
   __shared__ double apow[6][kNoiseThreads + 1];
   __shared__ double sh_w[kNoiseWarps];
-  const int64_t run = blockIdx.x / p.nseg;
-  const int seg = static_cast<int>(blockIdx.x % p.nseg);
-  const int64_t seg_lo = seg * p.seg_len;
-  const int64_t seg_hi = min64(p.n, seg_lo + p.seg_len);
+  const int segs = (p.pass == 1) ? p.nseg - 1 : p.nseg;
+  const int64_t run = blockIdx.x / segs;
+  const int seg = static_cast<int>(blockIdx.x % segs);
+  const int64_t seg_hi = min64(p.n, (seg + 1) * p.seg_len);
+  const int64_t seg_lo = (p.pass == 1) ? seg_hi - p.pass1_len : seg * p.seg_len;
   const int64_t grun = p.run_offset + run;
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
   const int i = threadIdx.x;
@@ -91,7 +96,14 @@ __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_c
     const int64_t t = tile0 + i;
     const bool live = t < seg_hi;
     double m[6], z[6];
-    if (live) {
+    if (live && p.pass == 1) {   // only the Gauss-Markov drives matter
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        z[c] = normal_pair(static_cast<uint32_t>(t), kDrawAccel + c, run_lo, run_hi, p.k0, p.k1).z0;
+        z[3 + c] = normal_pair(static_cast<uint32_t>(t), kDrawGyro + c, run_lo, run_hi, p.k0, p.k1).z0;
+        m[c] = m[3 + c] = 0.0;
+      }
+    } else if (live) {
       noisy_sample(p, p.ref_accel + t * 3, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo,
                    run_hi, run, phase, m, m + 3, z, z + 3);
     } else {
@@ -164,7 +176,7 @@ __global__ void noise_carry_kernel(NoiseParams p) {
   double cin = 0.0;
   for (int s = 0; s < p.nseg; ++s) {
     p.seg_carry[(run * p.nseg + s) * 6 + c] = cin;
-    cin = aL * cin + p.seg_end[(run * p.nseg + s) * 6 + c];
+    if (s + 1 < p.nseg) cin = aL * cin + p.seg_end[(run * p.nseg + s) * 6 + c];
   }
 }
 

@@ -186,6 +186,20 @@ def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetomete
     return out
 
 
+class _LazyDevice(dict):
+    """{'ref_gyro', 'ref_accel', 'ref_nav'} -> CUDA tensors, uploaded when first asked for."""
+
+    def __init__(self, sim):
+        super().__init__()
+        self._sim = sim
+
+    def __missing__(self, key):
+        sim = self._sim
+        src = sim._nav if key == 'ref_nav' else sim._traj[key]
+        self[key] = engine.to_device(src)
+        return self[key]
+
+
 class LazyRuns(Mapping):
     """dict-like {key: (n,3) array} of per-run histories, materialised on first access by
     re-running the requested runs with history output (deterministic Philox streams).
@@ -337,13 +351,11 @@ class Sim(object):
 
     @property
     def _dev(self):
-        """The trajectory on the device (made on first use: the single-GPU run() goes through
-        a plan that stages the host arrays itself)."""
+        """The trajectory on the device, each array uploaded on first use (the single-GPU run()
+        goes through a plan that stages the host arrays itself; the Allan path never needs the
+        [n][9] navigation rows)."""
         if self._dev_cache is None:
-            t = self._traj
-            self._dev_cache = {'ref_gyro': engine.to_device(t['ref_gyro']),
-                               'ref_accel': engine.to_device(t['ref_accel']),
-                               'ref_nav': engine.to_device(self._nav)}
+            self._dev_cache = _LazyDevice(self)
         return self._dev_cache
 
     # ---- run ----------------------------------------------------------------

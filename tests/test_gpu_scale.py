@@ -86,6 +86,14 @@ def test_k1_long_series_gm_carry(eng):
     og, oa = oracle_c.imu_noise(fs, gyro, accel, LOW_G, LOW_A, 5, np.arange(11, 11 + R))
     assert_close(g.cpu().numpy(), og, 1e-11, 1.0, 'gyro')
     assert_close(a.cpu().numpy(), oa, 1e-11, 1.0, 'accel')
+    # short correlation times only: the carry pass looks at the tail of each segment (the drives
+    # older than ~46 correlation times have decayed below 1e-20 of the state)
+    fast_g = dict(LOW_G, b_corr=np.array([0.5, 2.0, np.inf]))
+    fast_a = dict(LOW_A, b_corr=np.array([1.0, 1.0, 3.0]))
+    g, a = eng.imu_noise(fs, R, eng.to_device(gyro), eng.to_device(accel), fast_g, fast_a, 3, 40)
+    og, oa = oracle_c.imu_noise(fs, gyro, accel, fast_g, fast_a, 3, np.arange(40, 40 + R))
+    assert_close(g.cpu().numpy(), og, 1e-11, 1.0, 'gyro, truncated carry pass')
+    assert_close(a.cpu().numpy(), oa, 1e-11, 1.0, 'accel, truncated carry pass')
 
 
 def test_k4_allan_millions_of_samples(eng):

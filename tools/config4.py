@@ -26,13 +26,16 @@ def main():
     sim = Sim([fs, 0.0, 0.0], traj, ref_frame=1, imu=imu, algorithm=Allan(), seed=1)
     sim.run(2)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    sim.run(runs)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    times = []
+    for _ in range(2):      # the first pass also pays for the device allocations of the run blocks
+        t0 = time.perf_counter()
+        sim.run(runs)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = times[-1]
     ad = sim.get_data(['ad_gyro'])[0]['algo0_0']
     print(json.dumps({'config': 'BASELINE config 4', 'runs': runs, 'samples': n, 'channels': 6,
-                      'seconds': dt, 'sample_channels_per_s': runs * n * 6 / dt, 'ntau': int(ad.shape[0]),
+                      'seconds': dt, 'seconds_first_pass': times[0], 'sample_channels_per_s': runs * n * 6 / dt, 'ntau': int(ad.shape[0]),
                       'reference_estimate_core_hours': 3.7}))
 
 
