@@ -823,8 +823,9 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     const bool contiguous = !lp.level0 || sample_stride == 1;
     // the bulk copies need 16-byte aligned rows: always true for the decade sums (even pitch),
     // for the caller's series if the base and the row stride allow it
-    const bool aligned = !lp.level0 || (inner == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                                        (outer_stride & 1) == 0);
+    const bool aligned = lp.level0 ? (inner == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                                      (outer_stride & 1) == 0)
+                                   : (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
     if (contiguous && aligned) {
       // persistent kernel, every chunk of every series (the ragged last one is masked)
       lp.chunk_first = 0;
