@@ -625,7 +625,7 @@ int b2ins_mc_plan_create(int64_t n, int64_t max_runs, int ini_sets, int ini_rows
   p->ini_sets = ini_sets;
   p->ini_rows = ini_rows;
   const size_t in_bytes = p->in_doubles() * sizeof(double);
-  const size_t stage_bytes = (2 * p->n3p() + 9 + static_cast<size_t>(ini_sets) * ini_rows) * sizeof(double);
+  const size_t stage_bytes = (2 * p->n3p() + 10 + static_cast<size_t>(ini_sets) * ini_rows) * sizeof(double);
   const size_t out_bytes = (27 + static_cast<size_t>(max_runs) * 9) * sizeof(double);
   cudaError_t e = cudaGetDevice(&p->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
@@ -661,18 +661,19 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const dou
   const size_t n3p = plan->n3p();
   std::memcpy(plan->h_in, ref_gyro, n3 * sizeof(double));
   std::memcpy(plan->h_in + n3p, ref_accel, n3 * sizeof(double));
-  std::memcpy(plan->h_in + 2 * n3p, ref_nav_end, 9 * sizeof(double));
-  std::memcpy(plan->h_in + 2 * n3p + 9, ini, ini_d * sizeof(double));
+  // one slack double keeps the (virtual) base of the navigation rows 16-byte aligned
+  const size_t nav_at = 2 * n3p + ((static_cast<size_t>(n - 1) * 9) & 1);
+  std::memcpy(plan->h_in + nav_at, ref_nav_end, 9 * sizeof(double));
+  std::memcpy(plan->h_in + nav_at + 9, ini, ini_d * sizeof(double));
+  // the device block mirrors the staging block (gyro | accel | last nav row | ini): ONE copy.  The
+  // kernel only reads row n-1 of the navigation rows (end-point errors), so their base pointer is
+  // set n-1 rows below the staged row; the rest of the [n][9] block is never touched.
   double* d_gyro = plan->d_in;
   double* d_accel = plan->d_in + n3p;
-  double* d_nav = plan->d_in + 2 * n3p;
-  double* d_ini = d_nav + plan->n9p();
-  // the IMU block is contiguous on both sides: one copy; the nav row and ini are small
-  CU_CHECK(cudaMemcpyAsync(d_gyro, plan->h_in, (n3p + n3) * sizeof(double), cudaMemcpyHostToDevice,
-                           plan->stream));
-  CU_CHECK(cudaMemcpyAsync(d_nav + (n - 1) * 9, plan->h_in + 2 * n3p, 9 * sizeof(double),
-                           cudaMemcpyHostToDevice, plan->stream));
-  CU_CHECK(cudaMemcpyAsync(d_ini, plan->h_in + 2 * n3p + 9, ini_d * sizeof(double),
+  double* d_nav_end = plan->d_in + nav_at;
+  double* d_nav = d_nav_end - (n - 1) * 9;
+  double* d_ini = d_nav_end + 9;
+  CU_CHECK(cudaMemcpyAsync(d_gyro, plan->h_in, (nav_at + 9 + ini_d) * sizeof(double),
                            cudaMemcpyHostToDevice, plan->stream));
   double* d_stats = plan->d_out;
   double* d_err = plan->d_out + 27;

@@ -186,6 +186,27 @@ def trajectory_from_motion_def(fs, motion_def, ref_frame, mode=None, magnetomete
     return out
 
 
+class _DataDict(dict):
+    """Sim.data: a dict whose values may be registered as thunks and are built on first read."""
+
+    class _Thunk:
+        def __init__(self, fn):
+            self.fn = fn
+
+    def defer(self, key, fn):
+        dict.__setitem__(self, key, _DataDict._Thunk(fn))
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _DataDict._Thunk):
+            v = v.fn()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 class _LazyDevice(dict):
     """{'ref_gyro', 'ref_accel', 'ref_nav'} -> CUDA tensors, uploaded when first asked for."""
 
@@ -293,7 +314,7 @@ class Sim(object):
                     ok = False
                 if not ok:
                     raise ValueError('algorithm input or output is not a valid list or tuple.')
-        self.data = {}          # name -> ndarray | dict-of-runs | LazyRuns
+        self.data = _DataDict()  # name -> ndarray | dict-of-runs | LazyRuns (| thunk, until first read)
         self.err_stats = {}     # end-point ensemble statistics of the last run()
         self._traj = None
         self._dev_cache = None
@@ -331,7 +352,7 @@ class Sim(object):
         d['fs'], d['ref_frame'], d['time'] = self.fs[0], self.ref_frame, traj['time']
         d['ref_pos'], d['ref_vel'], d['ref_att_euler'] = traj['ref_pos'], traj['ref_vel'], traj['ref_att']
         d['ref_accel'], d['ref_gyro'] = traj['ref_accel'], traj['ref_gyro']
-        d['ref_att_quat'] = euler2quat_zyx(traj['ref_att'])
+        d.defer('ref_att_quat', lambda: euler2quat_zyx(traj['ref_att']))   # built when first read
         for k in ('ref_odo', 'gps_time', 'ref_gps', 'gps_visibility'):
             if k in traj:
                 d[k] = traj[k]
