@@ -38,32 +38,10 @@ struct NoiseParams {
   double* seg_end;
 };
 
-// inclusive scan of y_i = a y_{i-1} + x_i over the block (zero initial state).
-// apow[k] = a^k for k = 0..kNoiseThreads.  Returns y_i; *total = y_last (all threads).
-__device__ __forceinline__ double gm_block_scan(double x, const double* apow, double* sh_w,
-                                                double* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v = x;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const double u = __shfl_up_sync(0xffffffffu, v, off);
-    if (lane >= off) v += apow[off] * u;
-  }
-  if (lane == 31) sh_w[warp] = v;
-  __syncthreads();
-  // prefix over previous warps: P_w = sum_{q<w} a^{32 (w-1-q)} W_q
-  double pre = 0.0;
-  for (int q = 0; q < warp; ++q) pre = apow[32] * pre + sh_w[q];
-  double tot = 0.0;
-  for (int q = 0; q < kNoiseWarps; ++q) tot = apow[32] * tot + sh_w[q];
-  *total = tot;
-  __syncthreads();
-  return v + apow[lane + 1] * pre;
-}
-
-__global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
+__global__ void __launch_bounds__(kNoiseThreads, 2) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
   __shared__ double apow[6][kNoiseThreads + 1];
-  __shared__ double sh_w[kNoiseWarps];
+  __shared__ double sh_w[6][kNoiseWarps];     // inclusive warp totals of the six channels
+  __shared__ double sh_pre[6][kNoiseWarps + 1];   // zero-state value at the end of warps < w; [..][8] = tile
   const int segs = (p.pass == 1) ? p.nseg - 1 : p.nseg;
   const int64_t run = blockIdx.x / segs;
   const int seg = static_cast<int>(blockIdx.x % segs);
@@ -110,29 +88,49 @@ __global__ void __launch_bounds__(kNoiseThreads) imu_noise_kernel(const __grid_c
 #pragma unroll
       for (int c = 0; c < 6; ++c) m[c] = z[c] = 0.0;
     }
+    // The six Gauss-Markov recurrences d[t+1] = a d[t] + b z[t] as affine block scans, together:
+    // warp-level inclusive scans (shuffles with powers of a), the warp totals combined by 48
+    // threads, two barriers per tile.  y_i = sum_{q<=i} a^{i-q} b z_q (zero state at the tile
+    // start), d[tile0 + i] = a^i carry + y_{i-1}.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double y[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const TriadNoise& e = (c < 3) ? p.accel : p.gyro;
+      y[c] = e.gm_b[c % 3] * z[c];
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double u = __shfl_up_sync(0xffffffffu, y[c], off);
+        if (lane >= off) y[c] += apow[c][off] * u;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sh_w[c][warp] = y[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 * (kNoiseWarps + 1)) {
+      // thread (c, w): value at the end of warp w-1 from a zero state at the tile start
+      const int c = threadIdx.x / (kNoiseWarps + 1), w = threadIdx.x % (kNoiseWarps + 1);
+      double pre = 0.0;
+      for (int q = 0; q < w; ++q) pre = apow[c][32] * pre + sh_w[c][q];
+      sh_pre[c][w] = pre;
+    }
+    __syncthreads();
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       const TriadNoise& e = (c < 3) ? p.accel : p.gyro;
       const int a = c % 3;
-      // y_i = sum_{q<=i} a^{i-q} b z_q  ->  d[tile0+i+1] = a^{i+1} carry + y_i
-      double total;
-      const double y = gm_block_scan(e.gm_b[a] * z[c], apow[c], sh_w, &total);
-      const double y_prev = __shfl_up_sync(0xffffffffu, y, 1);
-      // d[tile0 + i]: needs y_{i-1}; lane 0 of a warp takes it from the previous warp
-      __shared__ double sh_last[kNoiseWarps];
-      if ((threadIdx.x & 31) == 31) sh_last[threadIdx.x >> 5] = y;
-      __syncthreads();
-      double ym1;
-      if (i == 0)
-        ym1 = 0.0;
-      else if ((threadIdx.x & 31) == 0)
-        ym1 = sh_last[(threadIdx.x >> 5) - 1];
-      else
-        ym1 = y_prev;
+      const double pre = sh_pre[c][warp];
+      const double yi = y[c] + apow[c][lane + 1] * pre;      // inclusive, whole tile
+      const double up = __shfl_up_sync(0xffffffffu, yi, 1);
+      const double ym1 = (lane == 0) ? pre : up;             // y_{i-1}; 0 for the first sample
       const double d = apow[c][i] * carry[c] + ym1;
       m[c] += d + e.wd[a] * z[c];
-      carry[c] = apow[c][kNoiseThreads] * carry[c] + total;
-      __syncthreads();
+      carry[c] = apow[c][kNoiseThreads] * carry[c] + sh_pre[c][kNoiseWarps];
     }
     if (live && p.pass == 0) {
       const int64_t o = run * p.osr + t * p.ost;

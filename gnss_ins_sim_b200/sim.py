@@ -528,7 +528,11 @@ class Sim(object):
         n = self._traj['ref_gyro'].shape[0]
         # runs per block: K1 materialises 48 B and K4 needs ~2 B of workspace per run-sample;
         # use up to a third of the free device memory
-        free_b = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 2 ** 31
+        if torch.cuda.is_available():    # free on the device + cached by torch's allocator but unused
+            free_b = (torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved()
+                      - torch.cuda.memory_allocated())
+        else:
+            free_b = 2 ** 31
         block = max(1, min(R, int(free_b / 3 // (n * 64)) or 1))
         tau_all, ada, adg = None, {}, {}
         for r0 in range(0, R, block):
