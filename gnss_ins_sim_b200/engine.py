@@ -358,6 +358,11 @@ def allan_num_tau(n, fs):
     return list(m[:k])
 
 
+def allan_taus(n, fs):
+    """tau [s] of the cluster sizes allan_var uses for n samples at fs (allan.py:37-43, :58)."""
+    return np.asarray(allan_num_tau(n, fs), dtype=np.float64) / float(fs)
+
+
 def allan(fs, x, n, nseries, inner=1, outer_stride=None, sample_stride=1):
     """K4.  x: CUDA f64 buffer holding `nseries` series of n samples; series s, sample t at
     x.flat[(s // inner) * outer_stride + (s % inner) + t * sample_stride].

@@ -523,8 +523,11 @@ class Sim(object):
                                 vib_accel=vib_acc, layout=layout)
 
     def _run_allan(self, i, algo):
+        """K1 (channel-major) + K4 for this rank's shard of the runs, in blocks sized to the free
+        device memory; the [R, ntau, 3] deviations of all ranks are gathered (a few hundred KB)."""
         name = self.algo_name(i)
         R = self.sim_count
+        lo, hi = self._shard
         n = self._traj['ref_gyro'].shape[0]
         # runs per block: K1 materialises 48 B and K4 needs ~2 B of workspace per run-sample;
         # use up to a third of the free device memory
@@ -533,20 +536,29 @@ class Sim(object):
                       - torch.cuda.memory_allocated())
         else:
             free_b = 2 ** 31
-        block = max(1, min(R, int(free_b / 3 // (n * 64)) or 1))
-        tau_all, ada, adg = None, {}, {}
-        for r0 in range(0, R, block):
-            r1 = min(R, r0 + block)
+        block = max(1, min(max(hi - lo, 1), int(free_b / 3 // (n * 64)) or 1))
+        tau_all, acc_blocks, gyr_blocks = None, [], []
+        for r0 in range(lo, hi, block):
+            r1 = min(hi, r0 + block)
             # every channel a contiguous series: K4 then streams them with bulk copies
             gyro, accel = self._noise_block(r0, r1, engine.LAYOUT_CHANNEL_MAJOR)
             tau, a, g = algo.run_batch(self.fs[0], accel, gyro, channel_major=True)
-            for r in range(r0, r1):
-                ada['%s_%d' % (name, r)] = a[r - r0]
-                adg['%s_%d' % (name, r)] = g[r - r0]
+            acc_blocks.append(a)
+            gyr_blocks.append(g)
             tau_all = tau
+        if tau_all is None:      # a rank without runs still needs tau for the gather below
+            tau_all = engine.allan_taus(n, self.fs[0])
+        ntau = len(tau_all)
+        a = np.concatenate(acc_blocks) if acc_blocks else np.zeros((0, ntau, 3))
+        g = np.concatenate(gyr_blocks) if gyr_blocks else np.zeros((0, ntau, 3))
+        if dist.world() > 1:
+            both = np.concatenate([a.reshape(hi - lo, -1), g.reshape(hi - lo, -1)], axis=1)
+            both = dist.gather_rows(torch.from_numpy(np.ascontiguousarray(both)), R)
+            a = both[:, :ntau * 3].reshape(R, ntau, 3)
+            g = both[:, ntau * 3:].reshape(R, ntau, 3)
         self.data['algo_time'] = {'%s_%d' % (name, r): tau_all for r in range(R)}
-        self.data['ad_accel'] = ada
-        self.data['ad_gyro'] = adg
+        self.data['ad_accel'] = {'%s_%d' % (name, r): a[r] for r in range(R)}
+        self.data['ad_gyro'] = {'%s_%d' % (name, r): g[r] for r in range(R)}
 
     def _run_foreign(self, i, algo):
         """Reference-style plugin run on the host, sensor data from K1

@@ -44,8 +44,13 @@ def _worker(rank, world, port, tmp):
     except Exception as e:          # symmetric memory unavailable on this box
         sys.stderr.write('P2PStats skipped: %s\n' % e)
         fused_ok = 0
+    # the Allan experiment shards its runs too (5 runs on 2 ranks) and gathers the deviations
+    from gnss_ins_sim_b200.allan_analysis import Allan
+    sa = Sim([100.0, 0.0, 0.0], traj, ref_frame=1, imu=imu, algorithm=Allan(), seed=7)
+    sa.run(5)
+    ad = np.stack([sa.get_data(['ad_gyro'])[0]['algo0_%d' % r] for r in range(5)])
     np.savez(os.path.join(tmp, 'r%d.npz' % rank), rows=allrows, local=mine.shape[0], fused=fused,
-             fused_ok=fused_ok,
+             fused_ok=fused_ok, ad_gyro=ad,
              proc=np.stack([ps['std']['algo0_%d' % r] for r in (0, 501, 1002)]), **st)
     td.destroy_process_group()
 
@@ -70,6 +75,10 @@ def test_sharded_runs_match_single_gpu(tmp_path):
     one = sim.get_error_stats('pos', -1)
     rows = sim.end_point_errors()
     ps = sim.get_error_stats('vel', err_stats_start=5.0)
+    from gnss_ins_sim_b200.allan_analysis import Allan
+    sa = Sim([100.0, 0.0, 0.0], traj, ref_frame=1, imu=imu, algorithm=Allan(), seed=7)
+    sa.run(5)
+    ad_one = np.stack([sa.get_data(['ad_gyro'])[0]['algo0_%d' % r] for r in range(5)])
     locals_ = []
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), 'r%d.npz' % r))
@@ -78,6 +87,7 @@ def test_sharded_runs_match_single_gpu(tmp_path):
         assert_close(z['rows'], rows, 1e-9, 1e-6, 'per-run errors')
         assert_close(z['proc'], np.stack([ps['std']['algo0_%d' % i] for i in (0, 501, 1002)]),
                      1e-9, 1e-9, 'process std')
+        assert_close(z['ad_gyro'], ad_one, 1e-12, 0.0, 'sharded Allan deviation')
         locals_.append(int(z['local']))
         if int(z['fused_ok']):
             full = np.stack([np.abs(rows).max(0), rows.mean(0), rows.std(0)])
