@@ -30,7 +30,7 @@ from collections.abc import Mapping
 import numpy as np
 import torch
 
-from . import engine, dist
+from . import engine, dist, logged
 from .free_integration import FreeIntegration
 from .free_integration_odo import FreeIntegration as FreeIntegrationOdo
 from .allan_analysis import Allan
@@ -317,6 +317,7 @@ class Sim(object):
         self.data = _DataDict()  # name -> ndarray | dict-of-runs | LazyRuns (| thunk, until first read)
         self.err_stats = {}     # end-point ensemble statistics of the last run()
         self._traj = None
+        self._logged = None      # data read from a logged-data directory (no sensor model)
         self._dev_cache = None
         self._cache = {}
 
@@ -333,9 +334,8 @@ class Sim(object):
             traj = load_trajectory(src)
         elif isinstance(src, str):
             if os.path.isdir(src):
-                raise NotImplementedError(
-                    'logged-data directories are read by the reference Sim; feed the arrays to '
-                    'FreeIntegration.run_batch / Allan.run_batch instead')
+                self._load_logged(src)
+                return
             traj = trajectory_from_motion_def(self.fs[0], src, self.ref_frame, self.mode,
                                               bool(self.imu and self.imu.magnetometer),
                                               bool(self.imu and self.imu.odo),
@@ -387,10 +387,12 @@ class Sim(object):
             num_times: run the simulation for num_times times with given IMU error model.
         '''
         self.sim_count = max(int(num_times), 1)
+        if self._traj is None and self._logged is None:
+            self._load_trajectory()
+        if self._logged is not None:
+            return self._run_logged()
         if self.imu is None:
             raise ValueError('imu must be an IMU model when data are generated from a trajectory')
-        if self._traj is None:
-            self._load_trajectory()
         self._cache = {}
         self.err_stats = {}
         self._mc = {}
@@ -415,6 +417,87 @@ class Sim(object):
                     self._run_allan(i, a)
                 else:
                     self._run_foreign(i, a)
+        self.sim_complete = True
+
+    # ---- logged data (ins_sim.py:415-451: data from files instead of pathgen) -------------------
+    def _load_logged(self, path):
+        """Every supported .csv of the directory in internal units; no sensor model is applied."""
+        d = logged.read_data_dir(os.path.abspath(path), self.ref_frame)
+        if 'time' not in d:
+            for v in d.values():
+                a = next(iter(v.values())) if isinstance(v, dict) else v
+                d['time'] = np.arange(a.shape[0]) / self.fs[0]
+                break
+        self._logged = d
+        self.data.update(d)
+        self.data['fs'], self.data['ref_frame'] = self.fs[0], self.ref_frame
+        if 'ref_att_euler' in d and 'ref_att_quat' not in d:
+            self.data.defer('ref_att_quat', lambda: euler2quat_zyx(d['ref_att_euler']))
+        # what the error statistics need of a trajectory
+        self._traj = {k2: d[k1] for k1, k2 in (('ref_pos', 'ref_pos'), ('ref_vel', 'ref_vel'),
+                                               ('ref_att_euler', 'ref_att'), ('time', 'time')) if k1 in d}
+
+    def _logged_sets(self, name):
+        """[R, n, ...] stack of the first sim_count sets (keys 0 .. R-1) of a per-run quantity."""
+        sets = self._logged.get(name)
+        if not isinstance(sets, dict):
+            raise ValueError('the data directory holds no %s-<key>.csv' % name)
+        try:
+            return np.stack([sets[r] for r in range(self.sim_count)])
+        except KeyError as e:
+            raise ValueError('the data directory holds no %s-%s.csv' % (name, e.args[0]))
+
+    def _run_logged(self):
+        """Algorithms on the logged sets 0 .. sim_count-1 (InsAlgoMgr.run_algo over the keys,
+        ins_algo_manager.py:73-95): one batched launch per algorithm, outputs keyed
+        '<algo>_<key>'; end-point error statistics if the directory has the reference files."""
+        import copy
+        self._cache, self.err_stats, self._mc = {}, {}, {}
+        R = self.sim_count
+        self._shard = (0, R)
+        d = self._logged
+        for i, a in enumerate(self.algo or []):
+            name = self.algo_name(i)
+            if isinstance(a, FreeIntegration):
+                self._mc[i] = {'base': a.run_times, 'end_err': None}
+                if isinstance(a, FreeIntegrationOdo):
+                    att, pos, vel = a.run_batch(self.ref_frame, self.fs[0], self._logged_sets('gyro'),
+                                                self._logged_sets('odo'))
+                else:
+                    att, pos, vel = a.run_batch(self.ref_frame, self.fs[0], self._logged_sets('gyro'),
+                                                self._logged_sets('accel'))
+                for out, arr in (('att_euler', att), ('pos', pos), ('vel', vel)):
+                    self.data[out] = dict(self.data[out]) if isinstance(self.data.get(out), dict) else {}
+                    self.data[out].update({'%s_%d' % (name, r): arr[r] for r in range(R)})
+                self.data['att_quat'] = DerivedRuns(self.data['att_euler'], euler2quat_zyx)
+                if all(k in d for k in ('ref_att_euler', 'ref_pos', 'ref_vel')):
+                    err = np.concatenate([
+                        (att[:, -1] - d['ref_att_euler'][-1] + math.pi) % (2.0 * math.pi) - math.pi,
+                        pos[:, -1] - d['ref_pos'][-1], vel[:, -1] - d['ref_vel'][-1]], axis=1)
+                    self._mc[i]['end_err'] = err
+                    self.err_stats[name] = engine.error_stats(engine.to_device(err)).cpu().numpy()
+            elif isinstance(a, Allan):
+                tau, ad_a, ad_g = a.run_batch(self.fs[0], self._logged_sets('accel'), self._logged_sets('gyro'))
+                self.data['algo_time'] = {'%s_%d' % (name, r): tau for r in range(R)}
+                self.data['ad_accel'] = {'%s_%d' % (name, r): ad_a[r] for r in range(R)}
+                self.data['ad_gyro'] = {'%s_%d' % (name, r): ad_g[r] for r in range(R)}
+            else:
+                outs = {o: {} for o in a.output}
+                for r in range(R):
+                    args = []
+                    for nm in a.input:
+                        v = self.data[nm] if nm in self.data else None
+                        if isinstance(v, dict):
+                            v = v.get(r)
+                        if v is None:
+                            raise ValueError('algorithm input %r is not in the data directory' % nm)
+                        args.append(v)
+                    a.reset()
+                    a.run(copy.deepcopy(args))
+                    for o, v in zip(a.output, a.get_results()):
+                        outs[o]['%s_%d' % (name, r)] = v
+                for o in a.output:
+                    self.data[o] = outs[o]
         self.sim_complete = True
 
     def _mc_config(self, ai, runs, r0, stats_start=-1, dump_runs=0):
@@ -709,6 +792,21 @@ class Sim(object):
                 start = int(idx[0])
             algo = self.algo[algo_index]
             lo, hi = self._shard
+            if self._logged is not None:
+                # the histories are on the host already (array_error + __array_stats,
+                # ins_data_manager.py:512-541, :797-808)
+                nm = self.algo_name(algo_index)
+                ps = np.zeros((self.sim_count, 3, 9))
+                for r in range(self.sim_count):
+                    k = '%s_%d' % (nm, r)
+                    e = np.concatenate([
+                        (self.data['att_euler'][k] - self._logged['ref_att_euler'] + math.pi) % (2.0 * math.pi)
+                        - math.pi,
+                        self.data['pos'][k] - self._logged['ref_pos'],
+                        self.data['vel'][k] - self._logged['ref_vel']], axis=1)[start:]
+                    ps[r] = np.stack([np.max(np.abs(e), 0), np.average(e, 0), np.std(e, 0)])
+                self._cache[key] = ps
+                return self._process_stats(algo_index, start_s, c0)
             d = self._dev
             ps = None
             if hi > lo:
@@ -743,7 +841,7 @@ class Sim(object):
         s += 'Reference frame: %s\n' % str(self.ref_frame)
         s += 'Simulation time duration: %s s\n' % str(len(self.data['time']) / self.fs[0])
         s += 'Simulation runs: %s\n' % str(self.sim_count)
-        has_mc = bool(getattr(self, '_mc', None))
+        has_mc = bool(getattr(self, '_mc', None)) and bool(self.err_stats)   # logged data may lack references
         if has_mc:
             s += '\n------------------------------------------------------------\n'
             s += 'The following are error statistics.'

@@ -37,3 +37,27 @@ def assert_close(x, ref, rel=1e-6, scale=1.0, what=''):
 
 def wrap_pi(x):
     return (np.asarray(x) + np.pi) % (2 * np.pi) - np.pi
+
+
+def write_logged_dir(path, g, deg=True):
+    """A logged-data directory in the reference's file format (demo_data_files/*): time.csv,
+    gyro-0.csv in deg/s, accel-0.csv, all-zero reference files, from a golden 'logged' fixture."""
+    os.makedirs(path, exist_ok=True)
+    n = g['gyro'].shape[0]
+    r2d = 180.0 / np.pi if deg else 1.0
+    gu = 'deg/s' if deg else 'rad/s'
+    np.savetxt(os.path.join(path, 'time.csv'), np.arange(n) / float(g['fs']), header='time (sec)', comments='')
+    np.savetxt(os.path.join(path, 'gyro-0.csv'), g['gyro'] * r2d, delimiter=',', comments='',
+               header='gyro_x (%s),gyro_y (%s),gyro_z (%s)' % (gu, gu, gu), fmt='%.18e')
+    np.savetxt(os.path.join(path, 'accel-0.csv'), g['accel'], delimiter=',', comments='',
+               header='accel_x (m/s^2),accel_y (m/s^2),accel_z (m/s^2)', fmt='%.18e')
+    z = np.zeros((n, 3))
+    np.savetxt(os.path.join(path, 'ref_pos.csv'), z, delimiter=',', comments='',
+               header='ref_pos_lat (deg),ref_pos_lon (deg),ref_pos_alt (m)')
+    np.savetxt(os.path.join(path, 'ref_vel.csv'), z, delimiter=',', comments='',
+               header='ref_vel_x (m/s),ref_vel_y (m/s),ref_vel_z (m/s)')
+    np.savetxt(os.path.join(path, 'ref_att_euler.csv'), z, delimiter=',', comments='',
+               header='ref_Yaw (deg),ref_Pitch (deg),ref_Roll (deg)')
+    with open(os.path.join(path, 'notes.txt'), 'w') as f:
+        f.write('not a data file')
+    return path

@@ -377,3 +377,31 @@ def test_path_gen_reproduces_the_bench_trajectory_and_errors():
                     np.array([[1.0, 100.0], [-1.0, 100.0], [-1.0, 100.0]]), pg.HIGH_MOBILITY, magnet=True)
     with pytest.raises(TypeError):
         pg.parse_mode(np.zeros(4))
+
+
+def test_logged_data_directory_loader(tmp_path):
+    """The reference Sim's file input (ins_sim.py:434-451, :508-559; sim_data.py:187-260): names and
+    keys from file names, units from the header row, conversion to internal units."""
+    from conftest import write_logged_dir
+    from gnss_ins_sim_b200 import logged
+    assert logged.name_and_key('Accel-12.CSV') == ('accel', 12)
+    assert logged.name_and_key('ref_pos.csv') == ('ref_pos', None)
+    assert logged.name_and_key('gyro-a.csv') == ('gyro', 'a')
+    assert logged.name_and_key('ini.txt') == (None, None)
+    g = load_golden('logged_bosch.npz')
+    d = write_logged_dir(str(tmp_path / 'log'), g)
+    assert logged.file_units(os.path.join(d, 'gyro-0.csv')) == ['deg/s'] * 3
+    data = logged.read_data_dir(d, 0)
+    assert sorted(data) == ['accel', 'gyro', 'ref_att_euler', 'ref_pos', 'ref_vel', 'time']
+    assert_close(data['gyro'][0], g['gyro'], 1e-15, 1e-9, 'gyro deg/s -> rad/s')
+    assert np.array_equal(data['accel'][0], g['accel'])
+    assert data['time'].shape == (1000,)
+    # an LLA position file in the virtual inertial frame becomes metres (ins_sim.py:809-825)
+    lla = np.array([[32.0, 120.0, 5.0], [32.00001, 120.00002, 6.0]])
+    xyz, units = logged.convert_pos(lla, ['deg', 'deg', 'm'], 1)
+    assert units == ['m', 'm', 'm']
+    ecef = onp.lla2ecef(lla * np.array([np.pi / 180, np.pi / 180, 1.0]))
+    assert_close(xyz[0], ecef[0], 1e-15, 1.0, 'first sample = its ECEF position')
+    assert abs(np.linalg.norm(xyz[1] - xyz[0]) - np.linalg.norm(ecef[1] - ecef[0])) < 1e-9
+    assert_close(logged.convert_units(np.array([[3600.0, 1.0, 2.0]]), ['deg/hr', 'rad/s', 'rad/s'],
+                                      ['rad/s'] * 3), [[np.pi / 180, 1.0, 2.0]], 1e-15, 0.0, 'deg/hr')

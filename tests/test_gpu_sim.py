@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_np as onp
-from conftest import GOLDEN, load_golden, assert_close, wrap_pi
+from conftest import GOLDEN, load_golden, assert_close, wrap_pi, write_logged_dir
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip('torch')
@@ -214,3 +214,35 @@ def test_gps_measurements_match_reference(gpu, rf):
     assert_close(sim.get_data(['gps_time'])[0], g['gps_time'], 1e-12, 1.0, 'gps_time')
     r = int(g['run_ids'][2])
     assert_close(sim.get_data(['gps'])[0][r], g['gps'][2], 1e-12, scale, 'gps history')
+
+
+@pytest.mark.parametrize('name', ['bosch', 'nxp'])
+def test_sim_on_a_logged_data_directory(gpu, tmp_path, name):
+    """demo_free_integration_openimu.py: Sim on a directory of logged .csv files (no IMU model),
+    FreeIntegration with the gravity override and earth_rot=False, against the reference's result
+    on the same data; error statistics against the (all-zero) reference files."""
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    from gnss_ins_sim_b200.allan_analysis import Allan
+    g = load_golden('logged_%s.npz' % name)
+    d = write_logged_dir(str(tmp_path / name), g)
+    algo = FreeIntegration(g['ini'], earth_rot=False)
+    sim = Sim([100.0, 0.0, 0.0], d, ref_frame=0, imu=None, algorithm=[algo, Allan()])
+    sim.run(1)
+    att, pos, vel = (sim.get_data([k])[0]['algo0_0'] for k in ('att_euler', 'pos', 'vel'))
+    assert np.abs(wrap_pi(att - g['att'])).max() < 1e-9
+    assert_close(pos, g['pos'], 1e-9, 1e-7, 'pos')
+    assert_close(vel, g['vel'], 1e-9, 1.0, 'vel')
+    st = sim.get_error_stats('vel', -1)
+    assert_close(st['max'], np.abs(g['vel'][-1]), 1e-9, 1e-9, 'end-point |error| vs a zero reference')
+    assert_close(st['std'], np.zeros(3), 0.0, 1e-12, 'one run: no spread')
+    ps = sim.get_error_stats('att_euler', err_stats_start=2.0)
+    assert_close(ps['max']['algo0_0'], np.abs(wrap_pi(g['att'][200:])).max(0), 1e-9, 1e-9, 'process max')
+    ned = sim.get_error_stats('pos', -1, extra_opt='ned')
+    assert ned['units'] == "['m', 'm', 'm']" and np.isfinite(ned['max']).all()
+    ad = sim.get_data(['ad_gyro'])[0]['algo1_0']
+    o, _ = onp.allan_var(g['gyro'][:, 2], 100.0)
+    assert_close(ad[:, 2], np.sqrt(o), 1e-9, 0.0, 'Allan deviation of the logged gyro z')
+    assert 'vel' in sim.results(err_stats_start=-1, extra_opt='ned')
+    with pytest.raises(ValueError):
+        sim.run(2)          # there is no gyro-1.csv
