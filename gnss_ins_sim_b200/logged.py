@@ -135,3 +135,61 @@ def read_data_dir(path, ref_frame):
         else:
             out.setdefault(name, {})[key] = data
     return out
+
+
+# ---- writing: Sim_data.save_to_file (sim_data.py:117-165) -----------------------------------------
+# name -> (column legends, internal units, units written to the file)
+_ANG3, _DEG3 = ['rad'] * 3, ['deg'] * 3
+OUTPUT_FORMAT = {
+    'time': (['time'], ['sec'], ['sec']),
+    'gps_time': (['gps_time'], ['sec'], ['sec']),
+    'gps_visibility': (['gps_visibility'], [''], ['']),
+    'ref_pos': (['ref_pos_lat', 'ref_pos_lon', 'ref_pos_alt'], ['rad', 'rad', 'm'], ['deg', 'deg', 'm']),
+    'ref_vel': (['ref_vel_x', 'ref_vel_y', 'ref_vel_z'], ['m/s'] * 3, ['m/s'] * 3),
+    'ref_att_euler': (['ref_Yaw', 'ref_Pitch', 'ref_Roll'], _ANG3, _DEG3),
+    'ref_att_quat': (['q0', 'q1', 'q2', 'q3'], [''] * 4, [''] * 4),
+    'ref_gyro': (['ref_gyro_x', 'ref_gyro_y', 'ref_gyro_z'], ['rad/s'] * 3, ['deg/s'] * 3),
+    'ref_accel': (['ref_accel_x', 'ref_accel_y', 'ref_accel_z'], ['m/s^2'] * 3, ['m/s^2'] * 3),
+    'ref_gps': (['ref_gps_lat', 'ref_gps_lon', 'ref_gps_alt', 'ref_gps_vN', 'ref_gps_vE', 'ref_gps_vD'],
+                ['rad', 'rad', 'm', 'm/s', 'm/s', 'm/s'], ['deg', 'deg', 'm', 'm/s', 'm/s', 'm/s']),
+    'ref_odo': (['ref_odo'], ['m/s'], ['m/s']),
+    'gyro': (['gyro_x', 'gyro_y', 'gyro_z'], ['rad/s'] * 3, ['deg/s'] * 3),
+    'accel': (['accel_x', 'accel_y', 'accel_z'], ['m/s^2'] * 3, ['m/s^2'] * 3),
+    'gps': (['gps_lat', 'gps_lon', 'gps_alt', 'gps_vN', 'gps_vE', 'gps_vD'],
+            ['rad', 'rad', 'm', 'm/s', 'm/s', 'm/s'], ['deg', 'deg', 'm', 'm/s', 'm/s', 'm/s']),
+    'odo': (['odo'], ['m/s'], ['m/s']),
+    'algo_time': (['algo_time'], ['sec'], ['sec']),
+    'pos': (['pos_lat', 'pos_lon', 'pos_alt'], ['rad', 'rad', 'm'], ['deg', 'deg', 'm']),
+    'vel': (['vel_x', 'vel_y', 'vel_z'], ['m/s'] * 3, ['m/s'] * 3),
+    'att_euler': (['Yaw', 'Pitch', 'Roll'], _ANG3, _DEG3),
+    'att_quat': (['q0', 'q1', 'q2', 'q3'], [''] * 4, [''] * 4),
+    'ad_gyro': (['AD_gyro_x', 'AD_gyro_y', 'AD_gyro_z'], ['rad/s'] * 3, ['deg/s'] * 3),
+    'ad_accel': (['AD_accel_x', 'AD_accel_y', 'AD_accel_z'], ['m/s^2'] * 3, ['m/s^2'] * 3),
+}
+
+
+def output_format(name, ref_frame):
+    legend, units, out_units = OUTPUT_FORMAT[name]
+    if ref_frame == 1 and name in ('ref_pos', 'pos'):        # ins_data_manager.py:207-230
+        legend = [name + '_' + c for c in 'xyz']
+        units = out_units = ['m', 'm', 'm']
+    if ref_frame == 1 and name in ('ref_gps', 'gps'):
+        legend = [name + '_' + c for c in ('x', 'y', 'z', 'vx', 'vy', 'vz')]
+        units = out_units = ['m', 'm', 'm', 'm/s', 'm/s', 'm/s']
+    return legend, units, out_units
+
+
+def write_data(path, name, data, ref_frame):
+    """`<name>.csv` or one `<name>-<key>.csv` per set, header `legend (unit)` per column, values in
+    the output units -- what the reference's results(data_dir) writes and its file input reads."""
+    legend, units, out_units = output_format(name, ref_frame)
+    header = ','.join('%s (%s)' % (l, u) if u else l for l, u in zip(legend, out_units))
+    os.makedirs(path, exist_ok=True)
+    written = []
+    items = data.items() if hasattr(data, 'items') else [(None, data)]
+    for key, arr in items:
+        fn = os.path.join(path, name + ('.csv' if key is None else '-%s.csv' % str(key)))
+        np.savetxt(fn, convert_units(np.asarray(arr), units, out_units), header=header, delimiter=',',
+                   comments='')
+        written.append(fn)
+    return written

@@ -723,6 +723,27 @@ class Sim(object):
         '''
         return [self.data[n] if n in self.data else None for n in data_names]
 
+    def save_data(self, data_dir, names=None, runs=None):
+        """Write data to `<data_dir>/<name>[-<key>].csv` in the reference's file format
+        (Sim_data.save_to_file, sim_data.py:117-165: output units, `legend (unit)` header), which
+        both Sims read back as a logged-data directory.  names: data names (default: everything
+        that has a file format); runs: keys of per-run data to write (default: all -- histories
+        are materialised by re-running blocks of runs, mind the count)."""
+        names = [n for n in self.data.keys() if n in logged.OUTPUT_FORMAT] if names is None else list(names)
+        written = []
+        for n in names:
+            if n not in self.data or n not in logged.OUTPUT_FORMAT:
+                raise KeyError('no file format for %r' % n)
+            v = self.data[n]
+            if isinstance(v, (dict, Mapping)):
+                keys = list(v.keys()) if runs is None else [k for k in v.keys()
+                                                          if k in runs or (isinstance(k, str) and
+                                                                           k.rsplit('_', 1)[-1].isdigit() and
+                                                                           int(k.rsplit('_', 1)[-1]) in runs)]
+                v = {k: v[k] for k in keys}
+            written += logged.write_data(data_dir, n, v, self.ref_frame)
+        return written
+
     def end_point_errors(self, algo_index=0):
         '''
         [R_local, 9] end-point errors (att wrapped [rad], pos, vel) of this rank's runs

@@ -405,3 +405,26 @@ def test_logged_data_directory_loader(tmp_path):
     assert abs(np.linalg.norm(xyz[1] - xyz[0]) - np.linalg.norm(ecef[1] - ecef[0])) < 1e-9
     assert_close(logged.convert_units(np.array([[3600.0, 1.0, 2.0]]), ['deg/hr', 'rad/s', 'rad/s'],
                                       ['rad/s'] * 3), [[np.pi / 180, 1.0, 2.0]], 1e-15, 0.0, 'deg/hr')
+
+
+def test_csv_files_round_trip(tmp_path):
+    """write_data (Sim_data.save_to_file format: output units, legend header) -> read_data_dir."""
+    from gnss_ins_sim_b200 import logged
+    rng = np.random.RandomState(3)
+    d = str(tmp_path / 'out')
+    gyro = {0: rng.randn(50, 3) * 0.01, 1: rng.randn(50, 3) * 0.01}
+    ref_pos = np.stack([0.55 + 1e-6 * rng.rand(50), 2.09 + 1e-6 * rng.rand(50), 10 * rng.rand(50)], 1)
+    files = logged.write_data(d, 'gyro', gyro, 0) + logged.write_data(d, 'ref_pos', ref_pos, 0) \
+        + logged.write_data(d, 'time', np.arange(50) / 100.0, 0)
+    assert sorted(os.path.basename(f) for f in files) == ['gyro-0.csv', 'gyro-1.csv', 'ref_pos.csv', 'time.csv']
+    assert open(files[0]).readline().strip() == 'gyro_x (deg/s),gyro_y (deg/s),gyro_z (deg/s)'
+    assert open(files[2]).readline().strip() == 'ref_pos_lat (deg),ref_pos_lon (deg),ref_pos_alt (m)'
+    back = logged.read_data_dir(d, 0)
+    assert_close(back['gyro'][1], gyro[1], 1e-15, 1e-18, 'gyro')
+    assert_close(back['ref_pos'], ref_pos, 1e-15, 0.0, 'ref_pos')
+    assert_close(back['time'], np.arange(50) / 100.0, 1e-15, 0.0, 'time')
+    # virtual inertial frame: positions are metres and stay as they are
+    xyz = rng.randn(50, 3) * 1e6
+    logged.write_data(d + '1', 'ref_pos', xyz, 1)
+    assert open(os.path.join(d + '1', 'ref_pos.csv')).readline().strip() == 'ref_pos_x (m),ref_pos_y (m),ref_pos_z (m)'
+    assert_close(logged.read_data_dir(d + '1', 1)['ref_pos'], xyz, 1e-15, 0.0, 'xyz')

@@ -246,3 +246,31 @@ def test_sim_on_a_logged_data_directory(gpu, tmp_path, name):
     assert 'vel' in sim.results(err_stats_start=-1, extra_opt='ned')
     with pytest.raises(ValueError):
         sim.run(2)          # there is no gyro-1.csv
+
+
+@pytest.mark.parametrize('rf', [0, 1])
+def test_saved_run_reads_back_as_logged_data(gpu, tmp_path, rf):
+    """Monte-Carlo run -> save_data (the reference's csv format) -> a second Sim on that directory:
+    the same algorithm on the read-back sensor data reproduces the histories and the statistics."""
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    g = load_golden('philox_90deg_mid_rf%d.npz' % rf)
+    imu = imu_model.IMU(accuracy='mid-accuracy', axis=6, gps=False)
+    sim = Sim([100.0, 0.0, 0.0], _traj(g), ref_frame=rf, imu=imu, algorithm=FreeIntegration(g['ini']),
+              seed=int(g['seed']))
+    sim.run(3)
+    d = str(tmp_path / 'saved')
+    files = sim.save_data(d, names=['time', 'ref_pos', 'ref_vel', 'ref_att_euler', 'gyro', 'accel'])
+    assert len(files) == 4 + 2 * 3
+    again = Sim([100.0, 0.0, 0.0], d, ref_frame=rf, imu=None, algorithm=FreeIntegration(g['ini']))
+    again.run(3)
+    for r in range(3):
+        k = 'algo0_%d' % r
+        assert np.abs(wrap_pi(again.get_data(['att_euler'])[0][k] - sim.get_data(['att_euler'])[0][k])).max() < 1e-9
+        assert_close(again.get_data(['pos'])[0][k], sim.get_data(['pos'])[0][k], 1e-9, 1.0 if rf == 1 else 1e-7, 'pos')
+        assert_close(again.get_data(['vel'])[0][k], sim.get_data(['vel'])[0][k], 1e-9, 1.0, 'vel')
+    for dn in ('att_euler', 'pos', 'vel'):
+        a, b = again.get_error_stats(dn, -1), sim.get_error_stats(dn, -1)
+        for kk in ('max', 'avg', 'std'):
+            assert_close(a[kk], b[kk], 1e-6, 1e-6 if dn != 'pos' or rf == 1 else 1e-9, '%s %s' % (dn, kk))
