@@ -849,8 +849,8 @@ class Sim(object):
         '''
         Simulation summary (ins_sim.py:194-251, :339-413): the configuration and the error
         statistics of att_euler / pos / vel in output units.  Returns the available data
-        names.  Saving every run to .csv / .kml is the reference's file export (out of
-        scope); data_dir saves summary.txt and the per-run end-point errors only.
+        names.  data_dir saves summary.txt; per-run data go to .csv files on request
+        (save_data: a Monte-Carlo experiment has thousands of runs); .kml export is out of scope.
         '''
         if not self.sim_complete:
             print("Call Sim.run() to run the simulaltion first.")
