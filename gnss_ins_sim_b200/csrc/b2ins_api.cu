@@ -134,10 +134,24 @@ void launch_mc_grf(const McParams& p, bool fed, bool proc, cudaStream_t s) {
     else
       mc_kernel<G, RF, true, false><<<grid, kThreads, 0, s>>>(p);
   } else {
-    if (proc)
+    if (proc) {
       mc_kernel<G, RF, false, true><<<grid, kThreads, 0, s>>>(p);
-    else
+    } else {
+      // wide lane groups are chosen when runs are few (one warp per SM sub-partition, the serial
+      // step latency-bound): there a second warp per group prepares the samples of the next block
+      // while the first integrates (B2INS_MC_SPEC=0 keeps the single-warp form)
+      if constexpr (G >= 8) {
+        static const bool spec = [] {
+          const char* e = std::getenv("B2INS_MC_SPEC");
+          return e == nullptr || e[0] != '0';
+        }();
+        if (spec) {
+          mc_kernel<G, RF, false, false, true><<<grid, 2 * kThreads, 0, s>>>(p);
+          return;
+        }
+      }
       mc_kernel<G, RF, false, false><<<grid, kThreads, 0, s>>>(p);
+    }
   }
 }
 
