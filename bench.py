@@ -51,10 +51,10 @@ WORKLOAD = ("free_integration, motion_def-90deg_turn.csv (n=1000 @100Hz), 'mid-a
 # FP64 thread-instructions (DFMA/DMUL/DADD/DSETP) one run-step costs in mc_kernel, by lane-group
 # width, from the ncu source-level counts in profiles/ncu_mc_kernel_r01_v5_*.json (lanes of a
 # group replicate the serial step, so wide groups spend more instructions per run-step)
-FP64_INST_PER_RUN_STEP = {16: 1969.8, 1: 634.3}
+FP64_INST_PER_RUN_STEP = {16: 1974.4, 1: 634.3}
 # dram__bytes_read.sum + dram__bytes_write.sum of one mc_kernel launch at this workload
-# (profiles/ncu_mc_kernel_r01_v5_cfg2_lanes16.json): the trajectory; the 72 KB of results stay in L2
-NCU_DRAM_BYTES_PER_LAUNCH = 135680
+# (profiles/ncu_mc_kernel_r01_v8_cfg2_lanes16_spec.json): the trajectory; the 72 KB of results stay in L2
+NCU_DRAM_BYTES_PER_LAUNCH = 135424
 
 
 def load_workload():
