@@ -115,10 +115,30 @@ int sm_count() {
 // are enough runs to give every SM sub-partition several warps; with fewer runs a wider
 // group buys latency (more warps in flight, phase A amortised over G samples).
 int auto_lanes(int64_t runs) {
-  // measured on B200 (profiles/probe_mc_r01_*.jsonl): the serial step is issue/latency bound
-  // per warp, so the best group width puts about one warp on every SM sub-partition --
-  // warps = runs*G/32 <= 4*SMs -- and never more lanes than that needs.
-  const int64_t smsp = static_cast<int64_t>(sm_count()) * 4;
+  // measured on B200 (profiles/probe_mc_r01_*.jsonl, profiles/spec_probe_r01.jsonl).
+  // Up to a few 10^4 runs the serial step is latency-bound per warp and the warp-specialised form
+  // (groups of 4 and more, one CTA of kWarps group-warps per SM) wins: its time is
+  // waves(G) x T_G with T_32 : T_16 : T_8 : T_4 = 0.60 : 0.67 : 0.78 : 1.0 (0.30, 0.335, 0.39, 0.50 ms
+  // per 1000 steps) -- take the cheapest, the wider group on ties.  4000 runs = one wave at G = 4
+  // (8e9 run-steps/s); G = 1 overtakes at about 4e4 runs (1.2e10 at 1e5, 1.66e10 at 1e6).
+  const int64_t sms = sm_count();
+  if (runs <= 40000) {
+    const int gs[4] = {32, 16, 8, 4};
+    const double cost[4] = {0.60, 0.67, 0.78, 1.0};
+    int best = 4;
+    double best_c = 1e300;
+    for (int i = 0; i < 4; ++i) {
+      const int64_t grid = (runs * gs[i] + 32 * kWarps - 1) / (32 * kWarps);
+      const double c = static_cast<double>((grid + sms - 1) / sms) * cost[i];
+      if (c < best_c) {
+        best_c = c;
+        best = gs[i];
+      }
+    }
+    return best;
+  }
+  // beyond that: about one warp per SM sub-partition, and never more lanes than that needs
+  const int64_t smsp = sms * 4;
   int g = 32;
   while (g > 1 && runs * g * 2 > smsp * 32 * 3) g >>= 1;   // warps <= 1.5 per sub-partition
   return g;
@@ -140,12 +160,18 @@ void launch_mc_grf(const McParams& p, bool fed, bool proc, cudaStream_t s) {
       // wide lane groups are chosen when runs are few (one warp per SM sub-partition, the serial
       // step latency-bound): there a second warp per group prepares the samples of the next block
       // while the first integrates (B2INS_MC_SPEC=0 keeps the single-warp form)
-      if constexpr (G >= 8) {
-        static const bool spec = [] {
+      // -- as long as the grid is one wave: the specialised CTAs are one per SM (8 warps of up to 255
+      // registers), a second wave would cost more than the overlap gains
+      if constexpr (G >= 4) {
+        static const int spec = [] {   // 0: never, 1 (default): one wave, 2: any grid
           const char* e = std::getenv("B2INS_MC_SPEC");
-          return e == nullptr || e[0] != '0';
+          return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
         }();
-        if (spec) {
+        // one wave, or a second wave that is at least a quarter full (a handful of CTAs over the SM
+        // count is cheaper co-resident in the single-warp form); groups of 4 gain enough (+38 %)
+        // to take the specialised form for any grid
+        const unsigned sms = static_cast<unsigned>(sm_count());
+        if (spec == 2 || (spec == 1 && (G == 4 || grid <= sms || 4 * grid >= 5 * sms))) {
           mc_kernel<G, RF, false, false, true><<<grid, 2 * kThreads, 0, s>>>(p);
           return;
         }

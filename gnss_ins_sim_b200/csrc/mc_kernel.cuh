@@ -265,7 +265,7 @@ struct MinBlocks {
   static constexpr int value = (G == 1) ? B2INS_G1_MINBLOCKS : (G == 2 ? 3 : 2);
 };
 
-// SPEC: the warp-specialised form for wide lane groups and few runs (one warp per SM
+// SPEC: the warp-specialised form for lane groups of 4 and more and few runs (one warp per SM
 // sub-partition, the serial step latency-bound with two thirds of its issue slots empty).  The
 // CTA has 2 x kWarps warps: warp w < kWarps PRODUCES the samples of block b+1 (noise, Gauss-Markov
 // scan: the time-parallel part) into one set of slots while warp w + kWarps INTEGRATES block b from
