@@ -114,7 +114,8 @@ int sm_count() {
 // roughly (A + G*B)/32 warp-instructions, so G = 1 is the throughput optimum once there
 // are enough runs to give every SM sub-partition several warps; with fewer runs a wider
 // group buys latency (more warps in flight, phase A amortised over G samples).
-int auto_lanes(int64_t runs) {
+// spec_ok: the launch can take the warp-specialised form (fused noise, end-point statistics only)
+int auto_lanes(int64_t runs, bool spec_ok) {
   // measured on B200 (profiles/probe_mc_r01_*.jsonl, profiles/spec_probe_r01.jsonl).
   // Up to a few 10^4 runs the serial step is latency-bound per warp and the warp-specialised form
   // (groups of 4 and more, one CTA of kWarps group-warps per SM) wins: its time is
@@ -122,7 +123,7 @@ int auto_lanes(int64_t runs) {
   // per 1000 steps) -- take the cheapest, the wider group on ties.  4000 runs = one wave at G = 4
   // (8e9 run-steps/s); G = 1 overtakes at about 4e4 runs (1.2e10 at 1e5, 1.66e10 at 1e6).
   const int64_t sms = sm_count();
-  if (runs <= 40000) {
+  if (spec_ok && runs <= 40000) {
     const int gs[4] = {32, 16, 8, 4};
     const double cost[4] = {0.60, 0.67, 0.78, 1.0};
     int best = 4;
@@ -305,7 +306,7 @@ static int free_integration_fed(int algo, int ref_frame, double fs, int64_t runs
   p.stats_start = -1;
   int lanes = lanes_per_run;
   if (lanes == 0) {
-    lanes = auto_lanes(runs);
+    lanes = auto_lanes(runs, false);
     // run-major rows are 24-byte strided per lane when G = 1; a wider group reads whole
     // contiguous stretches of one run
     if (layout == B2INS_LAYOUT_RUN_MAJOR && lanes < 8) lanes = 8;
@@ -577,7 +578,7 @@ int b2ins_mc_free_integration_f64(const b2ins_mc_config* cfg, const double* ref_
     p.out_odo = cfg->dump_odo;
     if (cfg->dump_odo && p.dump_runs == 0) p.dump_runs = cfg->dump_runs;
   }
-  const int lanes = cfg->lanes_per_run ? cfg->lanes_per_run : auto_lanes(cfg->runs);
+  const int lanes = cfg->lanes_per_run ? cfg->lanes_per_run : auto_lanes(cfg->runs, cfg->stats_start < 0);
   return launch_mc(p, lanes, cfg->ref_frame, false, cfg->stats_start >= 0,
                    static_cast<cudaStream_t>(stream));
 }
