@@ -81,6 +81,7 @@ SIGNATURES = {
     'b2ins_path_rows': (_L, [_P, _L, _D]),
     'b2ins_path_gen_host': (_L, [_P, _P, _L, _D, _D, _D, _D, _P, _I, _L, _P, _P, _P, c_int64_p, _P]),
     'b2ins_diag_dfma_rate': (_I, [c_double_p]),
+    'b2ins_diag_auto_lanes': (_I, [_L, _I, _I]),
 }
 
 _lib = None

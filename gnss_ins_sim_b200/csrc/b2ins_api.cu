@@ -115,14 +115,14 @@ int sm_count() {
 // are enough runs to give every SM sub-partition several warps; with fewer runs a wider
 // group buys latency (more warps in flight, phase A amortised over G samples).
 // spec_ok: the launch can take the warp-specialised form (fused noise, end-point statistics only)
-int auto_lanes(int64_t runs, bool spec_ok) {
+int auto_lanes(int64_t runs, bool spec_ok, int sm_override = 0) {
   // measured on B200 (profiles/probe_mc_r01_*.jsonl, profiles/spec_probe_r01.jsonl).
   // Up to a few 10^4 runs the serial step is latency-bound per warp and the warp-specialised form
   // (groups of 4 and more, one CTA of kWarps group-warps per SM) wins: its time is
   // waves(G) x T_G with T_32 : T_16 : T_8 : T_4 = 0.60 : 0.67 : 0.78 : 1.0 (0.30, 0.335, 0.39, 0.50 ms
   // per 1000 steps) -- take the cheapest, the wider group on ties.  4000 runs = one wave at G = 4
   // (8e9 run-steps/s); G = 1 overtakes at about 4e4 runs (1.2e10 at 1e5, 1.66e10 at 1e6).
-  const int64_t sms = sm_count();
+  const int64_t sms = sm_override > 0 ? sm_override : sm_count();
   if (spec_ok && runs <= 40000) {
     const int gs[4] = {32, 16, 8, 4};
     const double cost[4] = {0.60, 0.67, 0.78, 1.0};
@@ -954,6 +954,10 @@ __global__ void dfma_rate_kernel(double* out, int iters) {
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
   }
   out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int b2ins_diag_auto_lanes(int64_t runs, int fused, int sm_count_arg) {
+  return auto_lanes(runs < 1 ? 1 : runs, fused != 0, sm_count_arg);
 }
 
 int b2ins_diag_dfma_rate(double* dfma_per_s) {

@@ -308,6 +308,12 @@ int64_t b2ins_path_gen_host(const double* ini, const double* motion_def, int64_t
  * FP64 utilisation against (beside the HBM roofline).  Synchronous. */
 int b2ins_diag_dfma_rate(double* dfma_per_s);
 
+/* The lanes-per-run value lanes_per_run = 0 resolves to, for `runs` runs on `sm_count` SMs
+ * (0: the current device, 148 if there is none).  fused: the launch is the fused Monte-Carlo kernel
+ * with end-point statistics only (the warp-specialised form applies); otherwise supplied data or
+ * process statistics.  A pure function of its arguments: usable without a GPU. */
+int b2ins_diag_auto_lanes(int64_t runs, int fused, int sm_count);
+
 #ifdef __cplusplus
 }
 #endif

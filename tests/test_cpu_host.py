@@ -428,3 +428,18 @@ def test_csv_files_round_trip(tmp_path):
     logged.write_data(d + '1', 'ref_pos', xyz, 1)
     assert open(os.path.join(d + '1', 'ref_pos.csv')).readline().strip() == 'ref_pos_x (m),ref_pos_y (m),ref_pos_z (m)'
     assert_close(logged.read_data_dir(d + '1', 1)['ref_pos'], xyz, 1e-15, 0.0, 'xyz')
+
+
+def test_lanes_per_run_choice():
+    """lanes_per_run = 0: wide lane groups while runs are few (one-wave grids of the warp-specialised
+    kernel preferred), one lane per run for large ensembles; supplied data / process statistics keep
+    the one-warp-per-sub-partition rule.  Pure host logic (148 SMs given explicitly)."""
+    from gnss_ins_sim_b200 import _lib
+    lib = _lib.load()
+    pick = lambda runs, fused: lib.b2ins_diag_auto_lanes(runs, fused, 148)   # noqa: E731
+    assert [pick(r, 1) for r in (100, 500, 1000, 1200, 1500, 3000, 4000, 10000, 40000)] == \
+        [32, 32, 16, 8, 8, 4, 4, 4, 4]
+    assert pick(40001, 1) == 1 and pick(10 ** 6, 1) == 1
+    assert [pick(r, 0) for r in (500, 1000, 2000, 4000, 10000, 20000, 10 ** 6)] == [32, 16, 8, 4, 2, 1, 1]
+    # every choice is a width the kernels are instantiated for
+    assert all(pick(r, f) in (1, 2, 4, 8, 16, 32) for r in range(1, 60000, 997) for f in (0, 1))
