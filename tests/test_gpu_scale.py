@@ -129,6 +129,24 @@ def test_k4_allan_contiguous_series_both_front_ends(eng, n):
     assert_close(tau.cpu().numpy(), t, 1e-15, 0.0, 'tau')
 
 
+def test_lane_group_forms_agree_at_the_wave_boundary(eng):
+    """The same runs through every form of the fused kernel: 1200 runs are 150 CTAs at G = 16 (just
+    over one wave: the single-warp form is launched), 75 at G = 8 and 38 at G = 4 (warp-specialised
+    form), 10 at G = 1; automatic choice included.  Per-run end-point errors must agree."""
+    from conftest import load_golden
+    g = load_golden('traj_90deg_turn_100hz_rf1.npz')
+    nav = np.concatenate([g['ref_att'], g['ref_pos'], g['ref_vel']], axis=1)
+    dev = [eng.to_device(a) for a in (g['ref_gyro'], g['ref_accel'], nav, g['ini'][None])]
+    ref = None
+    for lanes in (1, 16, 8, 4, 0):
+        cfg = eng.make_mc_config(1, 100.0, nav.shape[0], 1200, 5, LOW_G, LOW_A, 1, 9, lanes_per_run=lanes)
+        err = eng.mc_free_integration(cfg, *dev).end_err.cpu().numpy()
+        if ref is None:
+            ref = err
+        else:
+            assert_close(err, ref, 1e-9, 1e-3, 'lanes %d' % lanes)
+
+
 def test_large_ensemble_properties(eng):
     """BASELINE-size ensembles without an oracle: (i) two disjoint halves of 2^16 runs have
     statistically identical error statistics, (ii) end-point std grows like the white-noise
