@@ -753,7 +753,11 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
   const size_t smem = (kAllanChunk + kAllanHalo + 1 + 16) * sizeof(double);
   const size_t smem_full = (kAllanRawLen + kAllanPadLen) * sizeof(double);
   const size_t smem_stream = (kAllanStages * kAllanRawLen + 2 * kAllanPadLen) * sizeof(double);
-  static bool attr_set = false;
+  // function attributes are per device: remember which devices have them
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  bool& attr_set = attr_done[dev];
   if (!attr_set) {
     if (cudaFuncSetAttribute(allan_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem)) != cudaSuccess)
