@@ -36,9 +36,10 @@ class McConfig(ctypes.Structure):
                 ('ini_sets', ctypes.c_int32), ('ini_rows', ctypes.c_int32),
                 ('lanes_per_run', ctypes.c_int32), ('stats_start', ctypes.c_int32),
                 ('dump_runs', ctypes.c_int64),
-                ('algo', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('algo', ctypes.c_int32), ('dump_stride', ctypes.c_int32),
                 ('odo_scale', ctypes.c_double), ('odo_stdv', ctypes.c_double),
-                ('ref_odo', ctypes.c_void_p), ('dump_odo', ctypes.c_void_p)]
+                ('ref_odo', ctypes.c_void_p), ('dump_odo', ctypes.c_void_p),
+                ('dump_quat', ctypes.c_void_p)]
 
 
 class B2insError(RuntimeError):
@@ -82,6 +83,7 @@ SIGNATURES = {
     'b2ins_path_gen_host': (_L, [_P, _P, _L, _D, _D, _D, _D, _P, _I, _L, _P, _P, _P, c_int64_p, _P]),
     'b2ins_diag_dfma_rate': (_I, [c_double_p]),
     'b2ins_diag_auto_lanes': (_I, [_L, _I, _I]),
+    'b2ins_diag_mc_shape': (_I, [_I, ctypes.POINTER(ctypes.c_int)]),
 }
 
 _lib = None
@@ -109,6 +111,13 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def mc_shape(lanes):
+    """'P,WI,split' of the fused Monte-Carlo launch for a lane-group width ('0' = single-warp form)."""
+    out = (ctypes.c_int * 3)()
+    check(load().b2ins_diag_mc_shape(int(lanes), out))
+    return '%d,%d,%d' % (out[0], out[1], out[2]) if out[0] else '0'
 
 
 def check(rc):

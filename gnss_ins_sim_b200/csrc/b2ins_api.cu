@@ -10,12 +10,28 @@
 
 #include "../../include/b2ins.h"
 #include "allan_kernel.cuh"
-#include "mc_kernel.cuh"
+#include "internal.h"
 #include "noise_kernel.cuh"
 #include "pathgen_host.h"
 #include "psd_kernel.cuh"
 #include "gps_kernel.cuh"
 #include "stats_kernel.cuh"
+
+#ifdef B2INS_SINGLE_TU
+#define B2_RF 0
+#define B2_PLAIN_NAME launch_mc_plain_rf0
+#define B2_SPEC_NAME launch_mc_spec_rf0
+#include "mc_plain_launch.cuh"
+#include "mc_spec_launch.cuh"
+#undef B2_RF
+#undef B2_PLAIN_NAME
+#undef B2_SPEC_NAME
+#define B2_RF 1
+#define B2_PLAIN_NAME launch_mc_plain_rf1
+#define B2_SPEC_NAME launch_mc_spec_rf1
+#include "mc_plain_launch.cuh"
+#include "mc_spec_launch.cuh"
+#endif
 
 using namespace b2ins;
 
@@ -109,97 +125,94 @@ int sm_count() {
   return cached;
 }
 
-// Lanes per run: the mechanization is serial in time, so the only parallelism is across
-// runs (and across the G samples of a block in phase A).  Instruction cost per run-step is
-// roughly (A + G*B)/32 warp-instructions, so G = 1 is the throughput optimum once there
-// are enough runs to give every SM sub-partition several warps; with fewer runs a wider
-// group buys latency (more warps in flight, phase A amortised over G samples).
-// spec_ok: the launch can take the warp-specialised form (fused noise, end-point statistics only)
-int auto_lanes(int64_t runs, bool spec_ok, int sm_override = 0) {
-  // measured on B200 (profiles/probe_mc_r01_*.jsonl, profiles/spec_probe_r01.jsonl).
-  // Up to a few 10^4 runs the serial step is latency-bound per warp and the warp-specialised form
-  // (groups of 4 and more, one CTA of kWarps group-warps per SM) wins: its time is
-  // waves(G) x T_G with T_32 : T_16 : T_8 : T_4 = 0.60 : 0.67 : 0.78 : 1.0 (0.30, 0.335, 0.39, 0.50 ms
-  // per 1000 steps) -- take the cheapest, the wider group on ties.  4000 runs = one wave at G = 4
-  // (8e9 run-steps/s); G = 1 overtakes at about 4e4 runs (1.2e10 at 1e5, 1.66e10 at 1e6).
-  const int64_t sms = sm_override > 0 ? sm_override : sm_count();
-  if (spec_ok && runs <= 40000) {
-    const int gs[4] = {32, 16, 8, 4};
-    const double cost[4] = {0.60, 0.67, 0.78, 1.0};
-    int best = 4;
-    double best_c = 1e300;
-    for (int i = 0; i < 4; ++i) {
-      const int64_t grid = (runs * gs[i] + 32 * kWarps - 1) / (32 * kWarps);
-      const double c = static_cast<double>((grid + sms - 1) / sms) * cost[i];
-      if (c < best_c) {
-        best_c = c;
-        best = gs[i];
-      }
-    }
-    return best;
+// tools: B2INS_MC_SHAPE="P,WI,split" overrides the specialised shape of the chosen G ("0" = the
+// single-warp form); read at every launch so that one process can sweep
+bool shape_override(McShape* sh) {
+  const char* e = std::getenv("B2INS_MC_SHAPE");
+  if (!e || !*e) return false;
+  int P = 0, WI = 0, split = 0;
+  const int got = std::sscanf(e, "%d,%d,%d", &P, &WI, &split);
+  if (got >= 1 && P == 0) {
+    sh->spec = false;
+    return true;
   }
-  // beyond that: about one warp per SM sub-partition, and never more lanes than that needs
+  if (got == 3) {
+    sh->P = P;
+    sh->WI = WI;
+    sh->split = split != 0;
+    sh->spec = true;
+    return true;
+  }
+  return false;
+}
+
+// The specialised shapes that are instantiated, by group width: four-warp CTAs (one SM sub-partition
+// per warp) where the group is narrow, the paired layout (producer and integrator of a group on the
+// same sub-partition) for the widest groups.
+McShape default_shape(int G) {
+  switch (G) {
+    case 1: return McShape{1, 6, 1, false, true};
+    case 2: return McShape{2, 6, 1, false, true};
+    case 4: return McShape{4, 6, 1, false, true};
+    case 8: return McShape{8, 6, 1, false, true};
+    case 16: return McShape{16, 1, 4, true, true};
+    default: return McShape{32, 1, 4, true, true};
+  }
+}
+
+// Lanes per run.  The recurrence is serial in time, so the only parallelism is across runs (and,
+// for the noise, across the samples and channels the producers take).  One integrator warp needs
+// ~370 cycles per step (ref_frame 1) whatever the number of runs it carries -- the dependent-issue
+// latency of a single warp -- so with few runs the narrowest group that still gives every SM a CTA
+// wins: fewer replicated lanes, one producer pass per G steps.  With many runs G = 1 is the throughput
+// form, and beyond ~2.6e5 runs the single-warp kernel (every warp generates and integrates, five CTAs
+// per SM) overtakes the specialised one.  Measured on B200 (profiles/spec2_probe_r02.jsonl, run-steps/s
+// at n = 1000, ref_frame 1): 500 runs G = 8 3.1e9; 1000 runs G = 4 5.4e9; 2000 / 4000 runs G = 2
+// 6.6e9 / 9.2e9; 8000 / 40 000 / 100 000 runs G = 1 1.06e10 / 1.22e10 / 1.27e10; 10^6 runs single-warp
+// form 1.79e10.
+// spec_ok: the launch can take the warp-specialised form (fused noise, end-point statistics only)
+constexpr int64_t kSpecMaxRunsG1 = int64_t(1) << 18;
+
+int auto_lanes(int64_t runs, bool spec_ok, int sm_override = 0) {
+  const int64_t sms = sm_override > 0 ? sm_override : sm_count();
+  if (spec_ok) {
+    // runs per CTA of the specialised shapes: 32 / G
+    if (runs <= sms * 4) return 8;
+    if (runs <= sms * 8) return 4;
+    if (runs <= sms * 32) return 2;
+    return 1;
+  }
+  // supplied data / process statistics (single-warp form): about one warp per SM sub-partition
   const int64_t smsp = sms * 4;
   int g = 32;
   while (g > 1 && runs * g * 2 > smsp * 32 * 3) g >>= 1;   // warps <= 1.5 per sub-partition
   return g;
 }
 
-template <int G, int RF>
-void launch_mc_grf(const McParams& p, bool fed, bool proc, cudaStream_t s) {
-  const int64_t runs_per_cta = static_cast<int64_t>(kWarps) * (32 / G);
-  const unsigned grid = static_cast<unsigned>((p.runs + runs_per_cta - 1) / runs_per_cta);
-  if (fed) {
-    if (proc)
-      mc_kernel<G, RF, true, true><<<grid, kThreads, 0, s>>>(p);
-    else
-      mc_kernel<G, RF, true, false><<<grid, kThreads, 0, s>>>(p);
-  } else {
-    if (proc) {
-      mc_kernel<G, RF, false, true><<<grid, kThreads, 0, s>>>(p);
-    } else {
-      // wide lane groups are chosen when runs are few (one warp per SM sub-partition, the serial
-      // step latency-bound): there a second warp per group prepares the samples of the next block
-      // while the first integrates (B2INS_MC_SPEC=0 keeps the single-warp form)
-      // -- as long as the grid is one wave: the specialised CTAs are one per SM (8 warps of up to 255
-      // registers), a second wave would cost more than the overlap gains
-      if constexpr (G >= 4) {
-        static const int spec = [] {   // 0: never, 1 (default): one wave, 2: any grid
-          const char* e = std::getenv("B2INS_MC_SPEC");
-          return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
-        }();
-        // one wave, or a second wave that is at least a quarter full (a handful of CTAs over the SM
-        // count is cheaper co-resident in the single-warp form); groups of 4 gain enough (+38 %)
-        // to take the specialised form for any grid
-        const unsigned sms = static_cast<unsigned>(sm_count());
-        if (spec == 2 || (spec == 1 && (G == 4 || grid <= sms || 4 * grid >= 5 * sms))) {
-          mc_kernel<G, RF, false, false, true><<<grid, 2 * kThreads, 0, s>>>(p);
-          return;
-        }
-      }
-      mc_kernel<G, RF, false, false><<<grid, kThreads, 0, s>>>(p);
+int launch_mc(const McParams& p, int lanes, int rf, bool fed, bool proc, cudaStream_t s) {
+  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+    return fail(B2INS_ERR_ARG, "lanes_per_run must be 0,1,2,4,8,16 or 32, got %d", lanes);
+  if (!fed && !proc && p.algo == 0 && !(lanes == 1 && p.runs >= kSpecMaxRunsG1 && !std::getenv("B2INS_MC_SHAPE"))) {
+    // fused noise, end-point results (and histories): the warp-specialised form
+#ifdef B2INS_PHASE_CLOCKS
+    if (const char* e = std::getenv("B2INS_MC_DEBUG")) const_cast<McParams&>(p).debug = std::atoi(e);
+#endif
+    McShape sh = default_shape(lanes);
+    shape_override(&sh);
+    if (sh.spec) {
+      sh.G = lanes;
+      const bool ok = (rf == 1) ? launch_mc_spec_rf1(p, sh, s) : launch_mc_spec_rf0(p, sh, s);
+      if (!ok)
+        return fail(B2INS_ERR_ARG, "no specialised kernel for lanes=%d P=%d WI=%d split=%d", sh.G, sh.P,
+                    sh.WI, static_cast<int>(sh.split));
+      CU_CHECK(cudaGetLastError());
+      return B2INS_OK;
     }
   }
-}
-
-template <int G>
-void launch_mc_g(const McParams& p, int rf, bool fed, bool proc, cudaStream_t s) {
   if (rf == 1)
-    launch_mc_grf<G, 1>(p, fed, proc, s);
+    launch_mc_plain_rf1(p, lanes, fed, proc, s);
   else
-    launch_mc_grf<G, 0>(p, fed, proc, s);
-}
-
-int launch_mc(const McParams& p, int lanes, int rf, bool fed, bool proc, cudaStream_t s) {
-  switch (lanes) {
-    case 1: launch_mc_g<1>(p, rf, fed, proc, s); break;
-    case 2: launch_mc_g<2>(p, rf, fed, proc, s); break;
-    case 4: launch_mc_g<4>(p, rf, fed, proc, s); break;
-    case 8: launch_mc_g<8>(p, rf, fed, proc, s); break;
-    case 16: launch_mc_g<16>(p, rf, fed, proc, s); break;
-    case 32: launch_mc_g<32>(p, rf, fed, proc, s); break;
-    default: return fail(B2INS_ERR_ARG, "lanes_per_run must be 0,1,2,4,8,16 or 32, got %d", lanes);
-  }
+    launch_mc_plain_rf0(p, lanes, fed, proc, s);
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }
@@ -303,6 +316,8 @@ static int free_integration_fed(int algo, int ref_frame, double fs, int64_t runs
   p.ost = p.st;
   p.osc = p.sc;
   p.dump_runs = runs;
+  p.dump_stride = 1;
+  p.dump_rows = n;
   p.stats_start = -1;
   int lanes = lanes_per_run;
   if (lanes == 0) {
@@ -562,8 +577,13 @@ int b2ins_mc_free_integration_f64(const b2ins_mc_config* cfg, const double* ref_
   p.out_vel = dump_vel;
   p.out_gyro = dump_gyro;
   p.out_accel = dump_accel;
-  layout_strides(B2INS_LAYOUT_RUN_MAJOR, cfg->dump_runs, cfg->n, &p.osr, &p.ost, &p.osc);
+  ARG_CHECK(cfg->dump_stride >= 0, "dump_stride must be >= 0");
+  p.dump_stride = cfg->dump_stride > 1 ? cfg->dump_stride : 1;
+  p.dump_rows = (cfg->n + p.dump_stride - 1) / p.dump_stride;
+  layout_strides(B2INS_LAYOUT_RUN_MAJOR, cfg->dump_runs, p.dump_rows, &p.osr, &p.ost, &p.osc);
   p.dump_runs = (dump_att || dump_gyro) ? cfg->dump_runs : 0;
+  ARG_CHECK(!cfg->dump_quat || dump_att, "dump_quat needs the attitude histories (dump_att)");
+  p.out_quat = cfg->dump_quat;
   p.end_err = end_err;
   p.end_state = end_state;
   p.proc_stats = proc_stats;
@@ -958,6 +978,18 @@ __global__ void dfma_rate_kernel(double* out, int iters) {
 
 int b2ins_diag_auto_lanes(int64_t runs, int fused, int sm_count_arg) {
   return auto_lanes(runs < 1 ? 1 : runs, fused != 0, sm_count_arg);
+}
+
+int b2ins_diag_mc_shape(int lanes_per_run, int* shape3) {
+  ARG_CHECK(shape3, "null output");
+  ARG_CHECK(lanes_per_run == 1 || lanes_per_run == 2 || lanes_per_run == 4 || lanes_per_run == 8 ||
+                lanes_per_run == 16 || lanes_per_run == 32, "lanes_per_run must be 1,2,4,8,16 or 32");
+  McShape sh = default_shape(lanes_per_run);
+  shape_override(&sh);   // (G = 1 launches of 2^18 runs and more take the single-warp form whatever this says)
+  shape3[0] = sh.spec ? sh.P : 0;
+  shape3[1] = sh.spec ? sh.WI : 0;
+  shape3[2] = (sh.spec && sh.split) ? 1 : 0;
+  return B2INS_OK;
 }
 
 int b2ins_diag_dfma_rate(double* dfma_per_s) {

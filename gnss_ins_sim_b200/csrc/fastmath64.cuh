@@ -67,7 +67,7 @@ B2_HD double b2_make(int32_t hi, int32_t lo) {
 // operands of DFMA/DMUL (c[3][off]) instead of being re-materialised with UMOV pairs inside
 // the time loop (the profile of the first build spent a fifth of its issue slots on UMOV).
 #ifdef __CUDACC__
-__constant__ double kB2Const[28] = {
+static __constant__ double kB2Const[28] = {
     1.58969099521155010221e-10,
     -2.50507602534068634195e-08,
     2.75573137070700676789e-06,
@@ -152,6 +152,22 @@ B2_HD double sqrt_nr(double x) {
   return x > 0.0 ? s : 0.0;
 #else
   return std::sqrt(x);
+#endif
+}
+
+// 1/sqrt(x) for normal x > 0: hardware seed + two Newton steps (within 1 ulp)
+B2_HD double rsqrt_nr(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = b2_fma(-h * y, y, 0.5);
+  y = b2_fma(y, e, y);
+  e = b2_fma(-h * y, y, 0.5);
+  y = b2_fma(y, e, y);
+  return y;
+#else
+  return 1.0 / std::sqrt(x);
 #endif
 }
 

@@ -78,13 +78,17 @@ struct McParams {
   double* out_gyro;
   double* out_accel;
   double* out_odo;     // [dump_runs][n] (algo 1)
+  double* out_quat;    // [dump_runs][rows][4] scalar-first quaternion of every kept attitude sample
   int64_t osr, ost, osc;
   int64_t dump_runs;
+  int64_t dump_stride; // >= 1: histories keep samples 0, s, 2s, ... (rows = ceil(n / s))
+  int64_t dump_rows;
   // per-run results
   double* end_err;     // [runs][9]
   double* end_state;   // [runs][9]
   double* proc_stats;  // [runs][3][9]
   int64_t stats_start;
+  int debug;           // tools (B2INS_PHASE_CLOCKS builds only): 1 = producers idle, 2 = integrators idle
 };
 
 // Prepared samples of one block, one slot per lane: phase A stores (gyro xyz, accel xyz),
@@ -215,6 +219,29 @@ __device__ __forceinline__ double gm_block(double x, double a, double apj, doubl
   return d;
 }
 
+// Row of sample t in the (possibly decimated) histories; false: the sample is not kept.
+__device__ __forceinline__ bool dump_row(const McParams& p, int64_t t, int64_t* row) {
+  if (p.dump_stride <= 1) {
+    *row = t;
+    return true;
+  }
+  const int64_t q = t / p.dump_stride;
+  *row = q;
+  return q * p.dump_stride == t;
+}
+
+// attitude.euler2quat, 'zyx' (attitude.py:188-205): [yaw, pitch, roll] -> scalar-first quaternion
+__device__ __forceinline__ void write_quat(double* q, double yaw, double pitch, double roll) {
+  double sy, cy, sp, cp, sr, cr;
+  sincos_angle(0.5 * yaw, &sy, &cy);
+  sincos_angle(0.5 * pitch, &sp, &cp);
+  sincos_angle(0.5 * roll, &sr, &cr);
+  q[0] = cy * cp * cr + sy * sp * sr;
+  q[1] = cy * cp * sr - sy * sp * cr;
+  q[2] = cy * sp * cr + sy * cp * sr;
+  q[3] = sy * cp * cr - cy * sp * sr;
+}
+
 // process-error accumulation of one sample (ins_data_manager.py:536-541, :761-808)
 __device__ __forceinline__ void proc_accumulate(const NavState& st, const double* r, double* pe_max,
                                                 double* pe_sum, double* pe_sq, double* pe_k,
@@ -319,7 +346,7 @@ mc_kernel(const __grid_constant__ McParams p) {
   {
     const int64_t irun = p.ini_offset + run;
     const int64_t set = (irun < p.ini_sets) ? irun : 0;  // free_integration.py:85-87
-    nav_init<RF>(st, p.ini + set * p.ini_rows, p.ini_rows);
+    nav_init<RF>(st, p.ini + set * p.ini_rows, p.ini_rows, p.dt);
   }
   // Gauss-Markov drift carried across blocks (d[0] = 0), and the powers a^j, a^G
   double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -349,6 +376,7 @@ mc_kernel(const __grid_constant__ McParams p) {
     p.out_vel[o] = st.vel.x;
     p.out_vel[o + p.osc] = st.vel.y;
     p.out_vel[o + 2 * p.osc] = st.vel.z;
+    if (p.out_quat) write_quat(p.out_quat + run * p.dump_rows * 4, st.yaw, st.pitch, st.roll);
   }
   // process-error accumulators (shifted sums: K = first error sample)
   double pe_max[9], pe_sum[9], pe_sq[9], pe_k[9];
@@ -428,14 +456,15 @@ mc_kernel(const __grid_constant__ McParams p) {
           mo = (tj < cnt) ? p.odo_scale * p.ref_odo[t] + p.odo_stdv * zo : 0.0;
         }
       }
-      if (warp_dumps && dump && tj < cnt && p.out_gyro) {
-        const int64_t o = run * p.osr + t * p.ost;
+      int64_t row;
+      if (warp_dumps && dump && tj < cnt && p.out_gyro && dump_row(p, t, &row)) {
+        const int64_t o = run * p.osr + row * p.ost;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           p.out_gyro[o + c * p.osc] = mg[c];
           p.out_accel[o + c * p.osc] = ma[c];
         }
-        if (odo_mode && p.out_odo) p.out_odo[run * p.n + t] = mo;
+        if (odo_mode && p.out_odo) p.out_odo[run * p.dump_rows + row] = mo;
       }
       if (odo_mode) {   // the odometer sample rides to phase B in the accel.x slot
         ma[0] = mo;
@@ -477,9 +506,12 @@ mc_kernel(const __grid_constant__ McParams p) {
           if (t0 + base + k >= p.stats_start)
             proc_accumulate(st, &sm.nav[s][(base + k) * 9], pe_max, pe_sum, pe_sq, pe_k, pe_cnt);
         }
-        nav_step<RF, kSplit>(st, w, f, p.dt, p.earth_rot != 0, role, odo_mode);
+        // exact trigonometry again after every kResync-th sample (a rule in absolute time: the same for
+        // every lane-group width)
+        const bool resync = ((t0 + base + k + 1) & (kResync - 1)) == 0;
+        nav_step<RF, kSplit, 2>(st, w, f, p.dt, p.earth_rot != 0, role, resync, odo_mode);
         if (hist && j == k) {
-          keep[0] = st.yaw; keep[1] = st.pitch; keep[2] = st.roll;
+          keep[0] = wrap_once(st.yaw); keep[1] = st.pitch; keep[2] = wrap_once(st.roll);
           keep[3] = st.pos.x; keep[4] = st.pos.y; keep[5] = st.pos.z;
           keep[6] = st.vel.x; keep[7] = st.vel.y; keep[8] = st.vel.z;
         }
@@ -502,14 +534,17 @@ mc_kernel(const __grid_constant__ McParams p) {
       B2_CLK(cb1);
       B2_ACC(3, cb0, cb1);
       // ---------------- histories: lane j writes the state of sample base+j+1 ---------
-      if (warp_dumps && dump && tj < cnt && p.out_att && t + 1 < p.n) {
-        const int64_t o = run * p.osr + (t + 1) * p.ost;
+      int64_t hrow;
+      if (warp_dumps && dump && tj < cnt && p.out_att && t + 1 < p.n && dump_row(p, t + 1, &hrow)) {
+        const int64_t row = hrow;
+        const int64_t o = run * p.osr + row * p.ost;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           p.out_att[o + c * p.osc] = keep[c];
           p.out_pos[o + c * p.osc] = keep[3 + c];
           p.out_vel[o + c * p.osc] = keep[6 + c];
         }
+        if (p.out_quat) write_quat(p.out_quat + (run * p.dump_rows + row) * 4, keep[0], keep[1], keep[2]);
       }
     }
 
@@ -540,7 +575,7 @@ mc_kernel(const __grid_constant__ McParams p) {
     }
     if (p.end_state) {
       double* e = p.end_state + run * 9;
-      e[0] = st.yaw; e[1] = st.pitch; e[2] = st.roll;
+      e[0] = wrap_once(st.yaw); e[1] = st.pitch; e[2] = wrap_once(st.roll);
       e[3] = st.pos.x; e[4] = st.pos.y; e[5] = st.pos.z;
       e[6] = st.vel.x; e[7] = st.vel.y; e[8] = st.vel.z;
     }

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kStatSmallThreads)
 stats_exchange_kernel(const __grid_constant__ XchgParams p) {
   __shared__ double sh[2 * kStatSmallThreads];
   __shared__ double loc[3 * kStatMaxComp + 1];
+  __shared__ int arrived[kXchgMaxWorld];   // 0: the peer's slot still holds an older call's values
   const int nc = p.ncomp;
   const int threads = (kStatSmallThreads / nc) * nc;
   const int c = threadIdx.x % nc;
@@ -212,11 +213,12 @@ stats_exchange_kernel(const __grid_constant__ XchgParams p) {
     const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer never launched
+      if (clock64() - t0 > 40000000000LL) {   // ~20 s: a peer never launched
         *p.timeout_flag = 1;
         break;
       }
     } while (seen < p.seq);
+    arrived[threadIdx.x] = seen >= p.seq;   // a stale slot (an older call's statistics) is never merged
   }
   __syncthreads();
   // ---- Chan merge of all shards, one thread per component, fixed rank order -------------------
@@ -226,7 +228,7 @@ stats_exchange_kernel(const __grid_constant__ XchgParams p) {
     for (int q = 0; q < p.world; ++q) {
       const double* sl = win + static_cast<int64_t>(q) * kXchgSlot;
       const double n_b = sl[3 * nc];
-      if (n_b <= 0.0) continue;
+      if (n_b <= 0.0 || !arrived[q]) continue;
       const double mean_b = sl[nc + c], std_b = sl[2 * nc + c];
       const double m2_b = std_b * std_b * n_b;
       if (n_a == 0.0) {

@@ -103,10 +103,18 @@ def fused_exchange(ncomp=9):
     rank must call this the same number of times: construction is collective)."""
     key = (ncomp, world())
     if key not in _p2p:
-        try:
-            _p2p[key] = P2PStats(ncomp) if initialised() and td.get_backend() == 'nccl' else None
-        except Exception:
-            _p2p[key] = None
+        obj = None
+        if initialised() and td.get_backend() == 'nccl':
+            try:
+                obj = P2PStats(ncomp)
+            except Exception:
+                obj = None
+            # all ranks or none: a rank on which the set-up failed must not leave the others spinning
+            ok = torch.tensor([1 if obj is not None else 0], dtype=torch.int32, device=_comm_device())
+            td.all_reduce(ok, op=td.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                obj = None
+        _p2p[key] = obj
     return _p2p[key]
 
 
@@ -202,6 +210,9 @@ class P2PStats:
 
     def timed_out(self):
         return bool(self.flag.item())
+
+    def reset_timeout(self):
+        self.flag.zero_()
 
 
 def ensemble_stats(end_err, total_runs):

@@ -140,13 +140,14 @@ class McResult:
         self.att = self.pos = self.vel = None   # [dump_runs,n,3]
         self.gyro = self.accel = None           # [dump_runs,n,3]
         self.odo = None                         # [dump_runs,n] (odometer variant)
+        self.quat = None                        # [dump_runs,rows,4] att_quat of the kept samples
         self.lanes_per_run = 0
 
 
 def make_mc_config(ref_frame, fs, n, runs, seed, gyro_err, accel_err, ini_sets, ini_rows,
                    earth_rot=True, run_offset=0, vib_gyro=None, vib_accel=None,
                    lanes_per_run=0, stats_start=-1, dump_runs=0, ini_offset=None,
-                   odo_err=None, ref_odo=None):
+                   odo_err=None, ref_odo=None, dump_stride=1):
     """odo_err {'scale','stdv'} + ref_odo (CUDA f64 [n]) select the odometer variant."""
     cfg = _lib.McConfig()
     cfg.ref_frame = int(ref_frame)
@@ -161,11 +162,13 @@ def make_mc_config(ref_frame, fs, n, runs, seed, gyro_err, accel_err, ini_sets, 
     cfg.accel_err = _lib.sensor_err(accel_err, 'vrw')
     cfg.vib_gyro = vib_gyro if isinstance(vib_gyro, _lib.Vib) else _lib.vib(vib_gyro)
     cfg.vib_accel = vib_accel if isinstance(vib_accel, _lib.Vib) else _lib.vib(vib_accel)
+    cfg._keep_vib = (vib_gyro, vib_accel)   # assignment copies the structs: keep the series tensors alive
     cfg.ini_sets = int(ini_sets)
     cfg.ini_rows = int(ini_rows)
     cfg.lanes_per_run = int(lanes_per_run)
     cfg.stats_start = int(stats_start)
     cfg.dump_runs = int(dump_runs)
+    cfg.dump_stride = int(dump_stride)
     cfg.algo = 0
     if odo_err is not None:
         assert ref_odo is not None and ref_odo.is_cuda and ref_odo.dtype == torch.float64
@@ -178,7 +181,7 @@ def make_mc_config(ref_frame, fs, n, runs, seed, gyro_err, accel_err, ini_sets, 
 
 
 def mc_free_integration(cfg, ref_gyro, ref_accel, ref_nav, ini, want_state=False,
-                        dump_nav=False, dump_imu=False, out=None):
+                        dump_nav=False, dump_imu=False, out=None, dump_quat=False):
     """K12: fused noise generation + free integration + per-run errors.
     ref_gyro, ref_accel [n,3]; ref_nav [n,9] (att,pos,vel); ini [S,rows]: CUDA f64.
     `out` may carry a preallocated McResult to reuse buffers."""
@@ -186,6 +189,7 @@ def mc_free_integration(cfg, ref_gyro, ref_accel, ref_nav, ini, want_state=False
     lib = _lib.load()
     dev = ref_gyro.device
     R, n, D = cfg.runs, cfg.n, cfg.dump_runs
+    rows = -(-n // max(1, cfg.dump_stride))          # histories keep every dump_stride-th sample
     res = out or McResult()
 
     def buf(cur, shape):
@@ -197,16 +201,18 @@ def mc_free_integration(cfg, ref_gyro, ref_accel, ref_nav, ini, want_state=False
     res.end_state = buf(res.end_state, (R, 9)) if want_state else None
     res.proc_stats = buf(res.proc_stats, (R, 3, 9)) if cfg.stats_start >= 0 else None
     if dump_nav and D > 0:
-        res.att, res.pos, res.vel = (buf(res.att, (D, n, 3)), buf(res.pos, (D, n, 3)),
-                                     buf(res.vel, (D, n, 3)))
+        res.att, res.pos, res.vel = (buf(res.att, (D, rows, 3)), buf(res.pos, (D, rows, 3)),
+                                     buf(res.vel, (D, rows, 3)))
+        res.quat = buf(res.quat, (D, rows, 4)) if dump_quat else None
     else:
-        res.att = res.pos = res.vel = None
+        res.att = res.pos = res.vel = res.quat = None
     if dump_imu and D > 0:
-        res.gyro, res.accel = buf(res.gyro, (D, n, 3)), buf(res.accel, (D, n, 3))
-        res.odo = buf(res.odo, (D, n)) if cfg.algo == 1 else None
+        res.gyro, res.accel = buf(res.gyro, (D, rows, 3)), buf(res.accel, (D, rows, 3))
+        res.odo = buf(res.odo, (D, rows)) if cfg.algo == 1 else None
     else:
         res.gyro = res.accel = res.odo = None
     cfg.dump_odo = res.odo.data_ptr() if res.odo is not None else None
+    cfg.dump_quat = res.quat.data_ptr() if res.quat is not None else None
     _lib.check(lib.b2ins_mc_free_integration_f64(
         ctypes.byref(cfg), _ptr(ref_gyro), _ptr(ref_accel), _ptr(ref_nav), _ptr(ini),
         _ptr(res.end_err), _ptr(res.end_state), _ptr(res.proc_stats),
@@ -348,6 +354,7 @@ def vib_series(series, N):
     v.type = _lib.VIB_SERIES
     v.series = series.data_ptr()
     v.series_len = int(N)
+    v._keep = series               # the device series lives as long as the Vib does
     return v
 
 

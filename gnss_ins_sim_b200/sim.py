@@ -394,6 +394,7 @@ class Sim(object):
         if self.imu is None:
             raise ValueError('imu must be an IMU model when data are generated from a trajectory')
         self._cache = {}
+        self._all_hist = None
         self.err_stats = {}
         self._mc = {}
         self._vib_acc = parse_env(self.env['acc'], self.fs[0]) if self.env and 'acc' in self.env else None
@@ -536,11 +537,13 @@ class Sim(object):
                 key = (sensor, runs, r0)
                 if key not in self._psd_cache:
                     n = self._traj['ref_gyro'].shape[0]
-                    self._psd_cache.clear() if len(self._psd_cache) > 8 else None
+                    if len(self._psd_cache) > 8:    # evict, but never a series of THIS (runs, r0) block:
+                        for k in [k for k in self._psd_cache if k[1:] != (runs, r0)]:   # its Vib is in use
+                            del self._psd_cache[k]
                     self._psd_cache[key] = engine.psd_series(self.fs[0], n, runs, sensor, v, self.seed,
                                                              self.run_base + r0)
                 series, N = self._psd_cache[key]
-                out.append(engine.vib_series(series, N))
+                out.append(engine.vib_series(series, N))   # the Vib keeps its series tensor alive
             else:
                 out.append(v)
         return out[0], out[1]
@@ -556,20 +559,31 @@ class Sim(object):
             # the plan path on this rank's shard (pinned staging, one H2D, K12, K3, one D2H);
             # with several ranks the [3][9] shard statistics are merged by one all_gather
             err, stats = np.zeros((0, 9)), np.zeros((3, 9))
-            p2p = dist.fused_exchange(9) if dist.world() > 1 and (hi - lo) * 9 <= (1 << 17) else None
+            # the exchange path is chosen from the LARGEST shard, a rank-independent quantity (shards
+            # differ by one run; every rank must take the same collective)
+            w = dist.world()
+            p2p = dist.fused_exchange(9) if w > 1 and -(-self.sim_count // w) * 9 <= (1 << 17) else None
             plan = None
             if hi > lo:
                 cfg = self._mc_config(i, hi - lo, lo)
                 t = self._traj
                 plan = engine.get_plan(cfg.n, cfg.runs, cfg.ini_sets, cfg.ini_rows)
+                if self._uses_psd():
+                    # K5 wrote the vibration series on torch's current stream; the plan runs K12 on
+                    # its own non-blocking stream: order the two
+                    torch.cuda.current_stream().synchronize()
                 err, stats = plan.run(cfg, t['ref_gyro'], t['ref_accel'], self._nav_end, algo.ini_sets,
                                       want_stats=p2p is None)
             self._mc[i]['end_err'] = err
             if p2p is not None:
                 # K3x on the plan's device buffer: statistics + NVLink exchange + merge, one kernel
                 # (plan.run has synchronised: the errors are final; torch's stream orders the copy)
-                merged = p2p(plan.err_device_ptr() if plan else None, hi - lo)
-                self.err_stats[name] = merged.cpu().numpy().copy()
+                merged = p2p(plan.err_device_ptr() if plan else None, hi - lo).cpu().numpy().copy()
+                if p2p.timed_out():      # a peer never arrived: the merge is incomplete, never use it
+                    p2p.reset_timeout()
+                    raise RuntimeError('statistics exchange (K3x) timed out waiting for a peer rank; '
+                                       'the ensemble statistics of this run() are not available')
+                self.err_stats[name] = merged
             else:
                 self.err_stats[name] = dist.combine_local_stats(stats, hi - lo)
         else:
@@ -675,6 +689,12 @@ class Sim(object):
     def _history(self, name, run):
         """(n,3) history of one run; materialises a block of neighbouring runs at once."""
         blk = run // self.history_block
+        whole = getattr(self, '_all_hist', None)      # histories() has pulled every run already
+        if whole is not None:
+            ai_w, lo_w, arrs = whole
+            key_w = name[1] if isinstance(name, tuple) and name[0] == ai_w else name
+            if isinstance(key_w, str) and key_w in arrs and 0 <= run - lo_w < arrs[key_w].shape[0]:
+                return arrs[key_w][run - lo_w]
         if isinstance(name, tuple):      # algorithm output (algo index, data name)
             ai, out = name
             key = ('nav', ai, blk)
@@ -707,11 +727,56 @@ class Sim(object):
                 if getattr(self, '_ref_gps_dev', None) is None:
                     self._ref_gps_dev = engine.to_device(self._traj['ref_gps'])
                 hist['gps'] = engine.gps_noise(r1 - r0, self._ref_gps_dev, self.imu.gps_err, self.ref_frame,
-                                               self.seed, run_offset=r0).cpu().numpy()
+                                               self.seed, run_offset=self.run_base + r0).cpu().numpy()
             else:
                 gyro, accel = self._noise_block(r0, r1)
                 hist.update({'gyro': gyro.cpu().numpy(), 'accel': accel.cpu().numpy()})
         return self._cache[key][name][run - blk * self.history_block]
+
+    def histories(self, algo_index=0, imu=False, stride=1, quat=False):
+        '''
+        Every run of this rank at once: {'att_euler', 'pos', 'vel'} -> [R_local, rows, 3] host arrays
+        (plus 'gyro', 'accel' with imu=True, 'att_quat' [R_local, rows, 4] with quat=True) -- what
+        the reference's Sim.run leaves in its data manager (ins_sim.py:184-187, att_quat associated
+        :729-794), here by ONE launch with history output for all runs and one device-to-host copy
+        per array into pinned memory.  stride > 1 keeps samples 0, stride, 2 stride, ... (rows =
+        ceil(n / stride), 'time' decimated alike): error histories of many runs for plotting without
+        72 bytes per run-step.  With stride 1 get_data() then serves single runs from these arrays.
+        '''
+        lo, hi = self._shard
+        algo = self.algo[algo_index]
+        if not isinstance(algo, FreeIntegration) or self._logged is not None:
+            raise ValueError('histories() is for the fused free-integration experiment')
+        runs = hi - lo
+        n = self._traj['ref_gyro'].shape[0]
+        out = {}
+        if runs == 0:
+            return {k: np.zeros((0, n, 3)) for k in ('att_euler', 'pos', 'vel')}
+        cfg = self._mc_config(algo_index, runs, lo, dump_runs=runs)
+        cfg.dump_stride = max(1, int(stride))
+        d = self._dev
+        res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'], algo.ini_device(),
+                                         dump_nav=True, dump_imu=imu, out=getattr(self, '_hist_res', None),
+                                         dump_quat=quat)
+        self._hist_res = res
+        pinned = getattr(self, '_hist_pinned', None)
+        names = [('att_euler', res.att), ('pos', res.pos), ('vel', res.vel)]
+        if imu:
+            names += [('gyro', res.gyro), ('accel', res.accel)]
+        if quat:
+            names += [('att_quat', res.quat)]
+        if pinned is None or any(k not in pinned or pinned[k].shape != t.shape for k, t in names):
+            pinned = {k: torch.empty(t.shape, dtype=torch.float64, pin_memory=True) for k, t in names}
+            self._hist_pinned = pinned
+        for k, t in names:
+            pinned[k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = {k: pinned[k].numpy() for k, _ in names}
+        if cfg.dump_stride == 1:
+            self._all_hist = (algo_index, lo, out)
+        else:
+            out['time'] = self.data['time'][::cfg.dump_stride]
+        return out
 
     # ---- results --------------------------------------------------------------
     def get_names_of_available_data(self):
@@ -853,7 +918,7 @@ class Sim(object):
         (save_data: a Monte-Carlo experiment has thousands of runs); .kml export is out of scope.
         '''
         if not self.sim_complete:
-            print("Call Sim.run() to run the simulaltion first.")
+            print("Sim.run() has not been called yet: nothing to summarise.")
             return None
         if gen_kml:
             raise NotImplementedError('kml export is the reference\'s kml_gen (out of scope)')

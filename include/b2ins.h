@@ -99,11 +99,16 @@ typedef struct b2ins_mc_config {
    * (demo_algorithms/free_integration_odo.py:63-160: body velocity = [odometer, 0, 0]) with
    * pathgen.odo_gen noise (pathgen.py:627-641): odo = odo_scale*ref_odo + odo_stdv*randn */
   int32_t algo;
-  int32_t reserved;
+  int32_t dump_stride;    /* histories keep samples 0, s, 2s, ... (rows = ceil(n / s)); 0 and 1 = every
+                             sample.  Decimated output for plotting error histories of many runs
+                             (Sim.plot / results(err_stats_start >= 0) territory, ins_sim.py:253-315) */
   double odo_scale;
   double odo_stdv;
   const double* ref_odo;  /* algo 1: DEVICE pointer [n], true forward speed (pathgen 'odo') */
   double* dump_odo;       /* algo 1, nullable: DEVICE pointer [dump_runs][n] odometer histories */
+  double* dump_quat;      /* nullable: DEVICE pointer [dump_runs][rows][4], the scalar-first quaternion of
+                             every kept attitude sample -- the att_quat the reference associates with each
+                             att_euler it holds (ins_sim.py:729-794, attitude.euler2quat :188-205) */
 } b2ins_mc_config;
 
 /* ---- housekeeping ------------------------------------------------------ */
@@ -171,7 +176,8 @@ int b2ins_imu_noise_f64_host(double fs, int64_t runs, int64_t n,
  *   end_state [runs][9] (nullable): att, pos, vel at sample n-1.
  *   proc_stats [runs][3][9] (nullable unless stats_start >= 0): per-run max|e|, mean, std
  *            (ddof 0) of the error over samples >= stats_start.
- *   dump_att/pos/vel, dump_gyro/accel (each nullable): [dump_runs][n][3] histories.
+ *   dump_att/pos/vel, dump_gyro/accel (each nullable): [dump_runs][rows][3] histories, rows = n or
+ *            ceil(n / cfg->dump_stride).
  * Asynchronous on `stream`. */
 int b2ins_mc_free_integration_f64(const b2ins_mc_config* cfg,
                                   const double* ref_gyro, const double* ref_accel,
@@ -313,6 +319,12 @@ int b2ins_diag_dfma_rate(double* dfma_per_s);
  * with end-point statistics only (the warp-specialised form applies); otherwise supplied data or
  * process statistics.  A pure function of its arguments: usable without a GPU. */
 int b2ins_diag_auto_lanes(int64_t runs, int fused, int sm_count);
+
+/* The launch shape of the fused, warp-specialised Monte-Carlo kernel for a lane-group width:
+ * shape3[0] = producer warps per integrator warp, [1] = integrator warps per CTA, [2] = 1 if the
+ * lanes of a group share the trigonometry of a step (0 for the single-warp form: all zero).
+ * Honours the tools' B2INS_MC_SHAPE override, i.e. reports what a launch would use.  Pure host logic. */
+int b2ins_diag_mc_shape(int lanes_per_run, int* shape3);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,10 @@ What is frozen:
                             reference's own gyro/accel and its att/pos/vel.
   philox_*.npz              the b2ins Philox normal stream (oracle_np.noise_normals)
                             injected into the reference's np.random.randn call
-                            sequence; reference outputs + end-point error stats.
+                            sequence; reference outputs + end-point error stats
+                            (string profiles, random / sinusoidal / PSD vibration, a dict
+                            IMU with white bias drift, the odometer variant).
+  ned_stats_*.npz           get_error_stats('pos', extra_opt='ned'|'ecef') of the reference.
   traj_*.npz                pathgen.path_gen output (true trajectory + ideal IMU).
   allan.npz, psd.npz        allan.allan_var / time_series_from_psd known answers.
 
@@ -192,6 +195,126 @@ def gen_philox(tag, motion, fs, accuracy, ref_frame, R, seed, env=None, run0=0):
                         accel_b=imu.accel_err['b'], accel_b_drift=imu.accel_err['b_drift'],
                         accel_b_corr=imu.accel_err['b_corr'], accel_vrw=imu.accel_err['vrw'],
                         **out, **extra)
+
+
+def gen_ned_stats(R=8, seed=12345):
+    """get_error_stats('pos', extra_opt='ned') of the reference (ins_data_manager.py:543-552) for the
+    philox_90deg_mid_rf0 experiment: LLA end-point errors expressed in metres in the local NED frame."""
+    csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
+    ini = read_ini(csv)
+    imu = fresh_imu('mid-accuracy')
+    sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=free_integration.FreeIntegration(ini))
+    n, run_ids = 1000, np.arange(R)
+    q = RandnQueue()
+    inject_stream(q, n, run_ids, seed)
+    real = np.random.randn
+    np.random.randn = q
+    try:
+        sim.run(R)
+    finally:
+        np.random.randn = real
+    assert not q.q
+    out = {'seed': seed, 'run_ids': run_ids}
+    for opt in ('ned', 'ecef'):
+        st = sim.dmgr.get_error_stats('pos', err_stats_start=-1, angle=False, use_output_units=False,
+                                      extra_opt=opt)
+        for k in ('max', 'avg', 'std'):
+            out['stat_pos_%s_%s' % (opt, k)] = np.asarray(st[k])
+    # the run must be the one frozen in philox_90deg_mid_rf0.npz
+    g = np.load(os.path.join(OUT, 'philox_90deg_mid_rf0.npz'))
+    assert np.array_equal(g['pos'][3], sim.dmgr.pos.data['algo0_3'])
+    np.savez_compressed(os.path.join(OUT, 'ned_stats_90deg_mid_rf0.npz'), **out)
+
+
+def gen_philox_white_drift(ref_frame, R=4, seed=31337):
+    """A dict-`accuracy` IMU without *_b_corr: the bias drift is white, drift[i]*randn(n) per axis
+    (pathgen.py:591-593) -- three (n,) draws per sensor instead of three (n,3) blocks; they are served
+    the GM-drive normals of the b2ins stream.  (The dict form writes into the module-level
+    'low-accuracy' tables, imu_model.py:110-143: restored afterwards.)"""
+    import copy
+    csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
+    ini = read_ini(csv)
+    saved = copy.deepcopy((imu_model.gyro_low_accuracy, imu_model.accel_low_accuracy))
+    acc = {'gyro_b': np.array([36.0, -20.0, 5.0]), 'gyro_arw': np.array([0.3, 0.25, 0.2]),
+           'gyro_b_stability': np.array([8.0, 6.0, 4.0]),
+           'accel_b': np.array([1e-3, -2e-3, 5e-4]), 'accel_vrw': np.array([0.04, 0.03, 0.05]),
+           'accel_b_stability': np.array([1e-4, 2e-4, 5e-5])}
+    try:
+        imu = imu_model.IMU(accuracy=acc, axis=6, gps=False)
+        assert np.all(np.isinf(imu.gyro_err['b_corr'])) and np.all(np.isinf(imu.accel_err['b_corr']))
+        errs = {k: np.array(v) for k, v in (
+            ('gyro_b', imu.gyro_err['b']), ('gyro_b_drift', imu.gyro_err['b_drift']),
+            ('gyro_b_corr', imu.gyro_err['b_corr']), ('gyro_arw', imu.gyro_err['arw']),
+            ('accel_b', imu.accel_err['b']), ('accel_b_drift', imu.accel_err['b_drift']),
+            ('accel_b_corr', imu.accel_err['b_corr']), ('accel_vrw', imu.accel_err['vrw']))}
+        sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu,
+                          algorithm=free_integration.FreeIntegration(ini))
+        n, run_ids = 1000, np.arange(R) + 2
+        z = onp.noise_normals(n, run_ids, seed)
+        q = RandnQueue()
+        for r in range(R):
+            for gm, w in ((z['acc_gm'], z['acc_w']), (z['gyr_gm'], z['gyr_w'])):
+                for i in range(3):
+                    q.push(gm[r, :, i])          # drift[i] * randn(n)
+                q.push(w[r])
+        real = np.random.randn
+        np.random.randn = q
+        try:
+            sim.run(R)
+        finally:
+            np.random.randn = real
+        assert not q.q
+        out = collect(sim, R)
+    finally:
+        imu_model.gyro_low_accuracy.clear()
+        imu_model.gyro_low_accuracy.update(saved[0])
+        imu_model.accel_low_accuracy.clear()
+        imu_model.accel_low_accuracy.update(saved[1])
+    np.savez_compressed(os.path.join(OUT, 'philox_90deg_whitedrift_rf%d.npz' % ref_frame), fs=100.0,
+                        ref_frame=ref_frame, ini=ini, seed=seed, run_ids=run_ids,
+                        **{'acc_' + k: v for k, v in acc.items()}, **errs, **out)
+
+
+def gen_philox_psd(ref_frame=1, R=3, seed=606):
+    """PSD vibration through the reference Sim: env = {'acc': table, 'gyro': table} (n,4) arrays
+    (ins_sim.py:642-701); acc_gen / gyro_gen call time_series_from_psd per axis after the bias-drift
+    blocks (pathgen.py:478-485, :541-548), each drawing randn(L) random phases -- served from the
+    b2ins stream (draws 16 + 3*sensor + axis)."""
+    csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
+    ini = read_ini(csv)
+    tab = np.genfromtxt(os.path.join(MOTION, 'vib_psd.csv'), delimiter=',', skip_header=1)
+    env_acc = tab.copy()
+    env_gyro = tab.copy()
+    env_gyro[:, 1:] *= 1e-4 * np.array([1.0, 0.5, 0.25])     # (rad/s)^2/Hz: a different table per axis
+    imu = fresh_imu('mid-accuracy')
+    sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=ref_frame, imu=imu,
+                      env={'acc': env_acc.copy(), 'gyro': env_gyro.copy()},
+                      algorithm=free_integration.FreeIntegration(ini))
+    n, run_ids = 1000, np.arange(R) + 10
+    L = n // 2 + 1
+    z = onp.noise_normals(n, run_ids, seed)
+    zp = {0: onp.psd_phase_normals(L, run_ids, seed, 0), 1: onp.psd_phase_normals(L, run_ids, seed, 1)}
+    q = RandnQueue()
+    for r in range(R):
+        for sensor, gm, w in ((0, z['acc_gm'], z['acc_w']), (1, z['gyr_gm'], z['gyr_w'])):
+            for i in range(3):
+                blk = np.full((n, 3), np.nan)
+                blk[:, i] = gm[r, :, i]
+                q.push(blk)
+            for i in range(3):
+                q.push(zp[sensor][r, i])
+            q.push(w[r])
+    real = np.random.randn
+    np.random.randn = q
+    try:
+        sim.run(R)
+    finally:
+        np.random.randn = real
+    assert not q.q
+    out = collect(sim, R)
+    np.savez_compressed(os.path.join(OUT, 'philox_90deg_mid_rf%d_psd.npz' % ref_frame), fs=100.0,
+                        ref_frame=ref_frame, ini=ini, seed=seed, run_ids=run_ids, env_acc=env_acc,
+                        env_gyro=env_gyro, **out)
 
 
 def gen_philox_odo(ref_frame, R=6, seed=4711):
@@ -379,6 +502,10 @@ def main():
     gen_philox('90deg_mid_rf0_vibsin', 'motion_def-90deg_turn.csv', 100.0, 'mid-accuracy', 0, 3,
                778, env={'acc': '[0.03 0.001 0.01]g-3Hz-sinusoidal',
                          'gyro': '[6 5 4]d-0.5Hz-sinusoidal'})
+    gen_ned_stats()
+    gen_philox_white_drift(1)
+    gen_philox_white_drift(0)
+    gen_philox_psd(1)
     gen_philox_odo(1)
     gen_philox_odo(0)
     gen_gps(0)

@@ -41,7 +41,8 @@ def test_abi_structs_match_header_layout():
     from gnss_ins_sim_b200 import _lib
     assert ctypes.sizeof(_lib.SensorErr) == 96
     assert ctypes.sizeof(_lib.Vib) == 48
-    assert ctypes.sizeof(_lib.McConfig) == 408
+    assert ctypes.sizeof(_lib.McConfig) == 416        # + dump_quat
+    assert _lib.McConfig.dump_stride.offset == 372 and _lib.McConfig.dump_quat.offset == 408
     assert _lib.McConfig.dump_runs.offset == 360 and _lib.McConfig.algo.offset == 368
     assert _lib.McConfig.ref_odo.offset == 392
 
@@ -431,15 +432,17 @@ def test_csv_files_round_trip(tmp_path):
 
 
 def test_lanes_per_run_choice():
-    """lanes_per_run = 0: wide lane groups while runs are few (one-wave grids of the warp-specialised
-    kernel preferred), one lane per run for large ensembles; supplied data / process statistics keep
-    the one-warp-per-sub-partition rule.  Pure host logic (148 SMs given explicitly)."""
+    """lanes_per_run = 0: the narrowest lane group that still gives every SM a CTA of the
+    warp-specialised kernel (32 / G runs per CTA), one lane per run for large ensembles; supplied data /
+    process statistics keep the one-warp-per-sub-partition rule.  Pure host logic (148 SMs given
+    explicitly)."""
     from gnss_ins_sim_b200 import _lib
     lib = _lib.load()
     pick = lambda runs, fused: lib.b2ins_diag_auto_lanes(runs, fused, 148)   # noqa: E731
-    assert [pick(r, 1) for r in (100, 500, 1000, 1200, 1500, 3000, 4000, 10000, 40000)] == \
-        [32, 32, 16, 8, 8, 4, 4, 4, 4]
+    assert [pick(r, 1) for r in (100, 500, 592, 593, 1000, 1184, 1185, 2000, 4000, 4736, 4737, 12500)] == \
+        [8, 8, 8, 4, 4, 4, 2, 2, 2, 2, 1, 1]
     assert pick(40001, 1) == 1 and pick(10 ** 6, 1) == 1
     assert [pick(r, 0) for r in (500, 1000, 2000, 4000, 10000, 20000, 10 ** 6)] == [32, 16, 8, 4, 2, 1, 1]
+    assert _lib.mc_shape(4) == '6,1,0' and _lib.mc_shape(32) == '1,4,1'
     # every choice is a width the kernels are instantiated for
     assert all(pick(r, f) in (1, 2, 4, 8, 16, 32) for r in range(1, 60000, 997) for f in (0, 1))

@@ -148,3 +148,49 @@ def test_gps_gen_oracle(rf):
     # the metre -> radian conversion really happened (LLA) / did not (xyz)
     sd = (out - g['ref_gps'][None]).std(axis=(0, 1))
     assert (sd[0] < 1e-5) == (rf == 0) and abs(sd[2] / 7.0 - 1) < 0.2 and abs(sd[4] / 0.05 - 1) < 0.2
+
+
+def _errs(g):
+    ge = {'b': g['gyro_b'], 'b_drift': g['gyro_b_drift'], 'b_corr': g['gyro_b_corr'], 'arw': g['gyro_arw']}
+    ae = {'b': g['accel_b'], 'b_drift': g['accel_b_drift'], 'b_corr': g['accel_b_corr'], 'vrw': g['accel_vrw']}
+    return ge, ae
+
+
+@pytest.mark.parametrize('rf', [0, 1])
+def test_white_bias_drift_branch_is_pinned(rf):
+    """b_corr = inf (a dict IMU without *_b_corr): drift[i]*randn(n), pathgen.py:591-593 -- both oracles
+    against the reference fed the same normals (philox_90deg_whitedrift_rf*.npz)."""
+    import oracle_c
+    g = load_golden('philox_90deg_whitedrift_rf%d.npz' % rf)
+    ge, ae = _errs(g)
+    assert np.all(np.isinf(ge['b_corr'])) and np.all(np.isinf(ae['b_corr']))
+    R = g['gyro'].shape[0]
+    for mod in (onp, oracle_c):
+        gyro, accel = mod.imu_noise(100.0, g['ref_gyro'], g['ref_accel'], ge, ae, int(g['seed']), g['run_ids'])
+        assert_close(gyro, g['gyro'], TIGHT, what='gyro')
+        assert_close(accel, g['accel'], TIGHT, what='accel')
+    att, pos, vel = onp.free_integration(rf, 100.0, g['gyro'], g['accel'], np.tile(g['ini'], (R, 1)))
+    assert_close(att, g['att'], 1e-10, what='att')
+    assert_close(vel, g['vel'], 1e-10, what='vel')
+
+
+def test_psd_vibration_through_the_reference_sim_is_pinned():
+    """env = PSD tables: the oracle's time_series_from_psd on the b2ins phase normals, added by
+    sensor_gen, equals what the reference Sim produced (philox_90deg_mid_rf1_psd.npz)."""
+    g = load_golden('philox_90deg_mid_rf1_psd.npz')
+    n, fs, seed = 1000, 100.0, int(g['seed'])
+    L = n // 2 + 1
+    z = onp.noise_normals(n, g['run_ids'], seed)
+    imu_g = {'b': np.zeros(3), 'b_drift': np.full(3, 3.5 * np.pi / 180 / 3600), 'b_corr': np.full(3, 100.0),
+             'arw': np.full(3, 0.25 * np.pi / 180 / 60)}
+    imu_a = {'b': np.zeros(3), 'b_drift': np.full(3, 5e-5), 'b_corr': np.full(3, 100.0), 'vrw': np.full(3, 0.03 / 60)}
+    for sensor, tab, ref, err, key, zg, zw, out in (
+            (0, g['env_acc'], g['ref_accel'], imu_a, 'vrw', z['acc_gm'], z['acc_w'], g['accel']),
+            (1, g['env_gyro'], g['ref_gyro'], imu_g, 'arw', z['gyr_gm'], z['gyr_w'], g['gyro'])):
+        m = np.where(tab[:, 0] > 0.5 * fs)[0][0]        # Sim.__parse_env cuts the table at fs/2
+        zp = onp.psd_phase_normals(L, g['run_ids'], seed, sensor)
+        for r in range(len(g['run_ids'])):
+            vib = np.stack([onp.time_series_from_psd(tab[:m, 1 + c], tab[:m, 0], fs, n, zp[r, c])[1]
+                            for c in range(3)], axis=1)
+            mea = onp.sensor_gen(fs, ref, err, key, zg[r:r + 1], zw[r:r + 1], vib=vib[None])[0]
+            assert_close(mea, out[r], 1e-11, what='sensor %d run %d' % (sensor, r))
