@@ -99,11 +99,15 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
+    if _build.stale():          # missing, or built from other sources than the ones in this tree
         try:
             _build.build()
-        except Exception as e:  # no nvcc on this box and no prebuilt library
-            raise B2insError('libb2ins.so is missing and could not be built: %s' % e)
+        except Exception as e:  # no nvcc on this box and no usable prebuilt library
+            if not os.path.exists(path):
+                raise B2insError('libb2ins.so is missing and could not be built: %s' % e)
+            raise B2insError('libb2ins.so was built from other sources and could not be rebuilt: %s' % e)
+    elif _build.LAST_BUILD == 'not checked':
+        _build.LAST_BUILD = 'reused'
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete

@@ -157,6 +157,9 @@ def load_trajectory(src):
         out['time'] = np.asarray(src['time'], dtype=np.float64)
     if 'ini' in src:
         out['ini'] = np.asarray(src['ini'], dtype=np.float64)
+    for k in ('gps_time', 'ref_gps', 'gps_visibility'):     # pathgen 'gps' rows, if the caller has them
+        if k in src:
+            out[k] = np.ascontiguousarray(src[k], dtype=np.float64)
     return out
 
 
@@ -755,19 +758,19 @@ class Sim(object):
         cfg = self._mc_config(algo_index, runs, lo, dump_runs=runs)
         cfg.dump_stride = max(1, int(stride))
         d = self._dev
+        pool = _hist_pool(self)      # device + pinned buffers: this Sim's, or a dead Sim's (never a live one's)
         res = engine.mc_free_integration(cfg, d['ref_gyro'], d['ref_accel'], d['ref_nav'], algo.ini_device(),
-                                         dump_nav=True, dump_imu=imu, out=getattr(self, '_hist_res', None),
-                                         dump_quat=quat)
-        self._hist_res = res
-        pinned = getattr(self, '_hist_pinned', None)
+                                         dump_nav=True, dump_imu=imu, out=pool.get('res'), dump_quat=quat)
+        pool['res'] = res
+        pinned = pool.setdefault('pinned', {})
         names = [('att_euler', res.att), ('pos', res.pos), ('vel', res.vel)]
         if imu:
             names += [('gyro', res.gyro), ('accel', res.accel)]
         if quat:
             names += [('att_quat', res.quat)]
-        if pinned is None or any(k not in pinned or pinned[k].shape != t.shape for k, t in names):
-            pinned = {k: torch.empty(t.shape, dtype=torch.float64, pin_memory=True) for k, t in names}
-            self._hist_pinned = pinned
+        for k, t in names:     # pinned staging is kept per process: pinning tens of MB costs milliseconds
+            if k not in pinned or pinned[k].shape != t.shape:
+                pinned[k] = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
         for k, t in names:
             pinned[k].copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -960,6 +963,25 @@ class Sim(object):
     def plot(self, what_to_plot, sim_idx=None, opt=None, extra_opt=''):
         raise NotImplementedError('plotting is the reference\'s sim_data_plot (matplotlib), out '
                                   'of scope: use get_data() and plot the arrays')
+
+
+# History staging (device buffers + pinned host tensors: tens of MB, milliseconds to pin) is handed from
+# a Sim that no longer exists to the next one that asks; a live Sim keeps its own, so the arrays
+# histories() returned stay valid as long as their Sim does.
+_HIST_POOLS = []      # [weakref to the owning Sim or None, dict]
+
+
+def _hist_pool(sim):
+    import weakref
+    for entry in _HIST_POOLS:
+        if entry[0] is not None and entry[0]() is sim:
+            return entry[1]
+    for entry in _HIST_POOLS:
+        if entry[0] is None or entry[0]() is None:
+            entry[0] = weakref.ref(sim)
+            return entry[1]
+    _HIST_POOLS.append([weakref.ref(sim), {}])
+    return _HIST_POOLS[-1][1]
 
 
 class _Merged(Mapping):

@@ -198,31 +198,36 @@ def gen_philox(tag, motion, fs, accuracy, ref_frame, R, seed, env=None, run0=0):
 
 
 def gen_ned_stats(R=8, seed=12345):
-    """get_error_stats('pos', extra_opt='ned') of the reference (ins_data_manager.py:543-552) for the
-    philox_90deg_mid_rf0 experiment: LLA end-point errors expressed in metres in the local NED frame."""
+    """get_error_stats('pos', extra_opt='ned' | 'ecef') of the reference (ins_data_manager.py:543-552)
+    for the philox_90deg_mid_rf0 experiment: LLA end-point errors in metres, in the local NED frame or
+    in ECEF.  The reference caches the error array of a data name at the first call
+    (ins_data_manager.py:427-431), so a second call with another option would return the first
+    option's numbers: every option gets a fresh Sim (first-call behaviour is what is frozen)."""
     csv = os.path.join(MOTION, 'motion_def-90deg_turn.csv')
     ini = read_ini(csv)
-    imu = fresh_imu('mid-accuracy')
-    sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=free_integration.FreeIntegration(ini))
     n, run_ids = 1000, np.arange(R)
-    q = RandnQueue()
-    inject_stream(q, n, run_ids, seed)
-    real = np.random.randn
-    np.random.randn = q
-    try:
-        sim.run(R)
-    finally:
-        np.random.randn = real
-    assert not q.q
     out = {'seed': seed, 'run_ids': run_ids}
+    g = np.load(os.path.join(OUT, 'philox_90deg_mid_rf0.npz'))
     for opt in ('ned', 'ecef'):
+        imu = fresh_imu('mid-accuracy')
+        sim = ins_sim.Sim([100.0, 0.0, 0.0], csv, ref_frame=0, imu=imu,
+                          algorithm=free_integration.FreeIntegration(ini))
+        q = RandnQueue()
+        inject_stream(q, n, run_ids, seed)
+        real = np.random.randn
+        np.random.randn = q
+        try:
+            sim.run(R)
+        finally:
+            np.random.randn = real
+        assert not q.q
+        # the run must be the one frozen in philox_90deg_mid_rf0.npz
+        assert np.array_equal(g['pos'][3], sim.dmgr.pos.data['algo0_3'])
         st = sim.dmgr.get_error_stats('pos', err_stats_start=-1, angle=False, use_output_units=False,
                                       extra_opt=opt)
         for k in ('max', 'avg', 'std'):
             out['stat_pos_%s_%s' % (opt, k)] = np.asarray(st[k])
-    # the run must be the one frozen in philox_90deg_mid_rf0.npz
-    g = np.load(os.path.join(OUT, 'philox_90deg_mid_rf0.npz'))
-    assert np.array_equal(g['pos'][3], sim.dmgr.pos.data['algo0_3'])
+    assert not np.allclose(out['stat_pos_ned_std'], out['stat_pos_ecef_std'])
     np.savez_compressed(os.path.join(OUT, 'ned_stats_90deg_mid_rf0.npz'), **out)
 
 
