@@ -474,6 +474,7 @@ def run_b200(args):
     extra['config3'] = config3_block(world, rank, args, dfma.value)
     if world == 1 and not args.no_config4:
         extra['config4'] = config4_block()
+    extra['config5'] = config5_block(world, rank, args)
     if world > 1 and rank == 0:
         bad = [k for k, v in (('config2', parity), ('config3', extra['config3'].get('multi_gpu_parity')))
                if v and (v.get('k3x_timed_out') or v.get('max_rel_diff', 0.0) > 1e-9)]
@@ -623,6 +624,55 @@ def config4_block():
             'api': 'Sim.run(256) with the Allan plugin (device noise generation + tau-binning)'}
 
 
+def config5_block(world, rank, args):
+    """BASELINE config 5: loosely-coupled 15-state GNSS/INS filter, motion_def-ins.csv @100 Hz with GPS at
+    10 Hz (n = 73 250, 7 325 GPS samples), demo_ins_loose.py's IMU, 10 000 runs sharded over the ranks.
+    The reference algorithm is a stub, so parity is unpinned: the record carries the filter's consistency
+    (NEES, 3-sigma containment) beside the time."""
+    import torch
+    import torch.distributed as td
+    from gnss_ins_sim_b200 import imu_model, dist
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.ins_loose import InsLoose
+    runs_total = args.c5_runs
+    acc = {'gyro_b': np.zeros(3), 'gyro_arw': np.array([0.25, 0.25, 0.25]),
+           'gyro_b_stability': np.array([3.5, 3.5, 3.5]), 'gyro_b_corr': np.array([100.0, 100.0, 100.0]),
+           'accel_b': np.zeros(3), 'accel_vrw': np.array([0.03119, 0.03009, 0.04779]),
+           'accel_b_stability': np.array([4.29e-5, 5.72e-5, 8.02e-5]),
+           'accel_b_corr': np.array([200.0, 200.0, 200.0])}               # demo_ins_loose.py:28-37
+    imu = imu_model.IMU(accuracy=acc, axis=6, gps=True)
+    csv = os.path.join(ROOT, 'tests', 'golden', 'motion_def-ins.csv')
+    t0 = time.perf_counter()
+    sim = Sim([100.0, 10.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=InsLoose(), seed=5)
+    sim.run(min(64 * world, runs_total))                 # trajectory, uploads, kernel load
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    if world > 1:
+        td.barrier()
+    t0 = time.perf_counter()
+    sim.run(runs_total)
+    torch.cuda.synchronize()
+    dt_local = time.perf_counter() - t0
+    t = torch.tensor([dt_local], dtype=torch.float64, device='cuda')
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    dt = float(t.item())
+    n = sim.data['time'].shape[0]
+    c = sim.ekf_consistency()
+    st = sim.get_error_stats('pos', -1, extra_opt='ned')
+    return {'workload': 'ins_loose 15-state loosely-coupled GNSS/INS EKF, motion_def-ins.csv (n=%d @100Hz, GPS '
+                        '@10Hz), %d MC runs sharded over %d GPU(s)' % (n, runs_total, world),
+            'runs': runs_total, 'samples': n, 'seconds_max_over_ranks': dt, 'run_steps_per_s': runs_total * n / dt,
+            'setup_s_path_gen_upload_warmup': t_setup,
+            'parity': 'unpinned: the reference algorithm is a stub (ins_loose.py:124-134); kernel == spec in '
+                      'tests/test_ekf.py',
+            'consistency_this_rank': {'nees_pos_vel_att_mean': c['nees'].mean(0).tolist(),
+                                      'inside_3sigma_min_over_states': float(c['inside3'].mean(0).min()),
+                                      'gps_epochs': c['epochs']},
+            'end_point_pos_ned_std_m': np.asarray(st['std']).tolist(),
+            'api': 'Sim.run(%d) with the InsLoose plugin' % runs_total}
+
+
 def main():
     # Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON
     # line on stdout, so everything else is sent to stderr and the line is written to the saved fd.
@@ -640,6 +690,7 @@ def main():
                     help='device-timed part only (for runs under a profiler): no e2e, no cpu baseline')
     ap.add_argument('--c3-runs', type=int, default=C3_RUNS, help='Monte-Carlo runs of the config-3 block')
     ap.add_argument('--no-config4', action='store_true')
+    ap.add_argument('--c5-runs', type=int, default=10000, help='Monte-Carlo runs of the config-5 block')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

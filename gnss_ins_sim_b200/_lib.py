@@ -42,6 +42,16 @@ class McConfig(ctypes.Structure):
                 ('dump_quat', ctypes.c_void_p)]
 
 
+class EkfConfig(ctypes.Structure):
+    _fields_ = [('fs', ctypes.c_double), ('n', ctypes.c_int64), ('runs', ctypes.c_int64),
+                ('run_offset', ctypes.c_int64), ('m', ctypes.c_int64), ('seed', ctypes.c_uint64),
+                ('gyro_err', SensorErr), ('accel_err', SensorErr),
+                ('gps_stdp', ctypes.c_double * 3), ('gps_stdv', ctypes.c_double * 3),
+                ('ini', ctypes.c_double * 9), ('ini_att_std', ctypes.c_double * 3),
+                ('stats_start', ctypes.c_int64), ('dump_runs', ctypes.c_int64),
+                ('dump_stride', ctypes.c_int32), ('earth_rot', ctypes.c_int32)]
+
+
 class B2insError(RuntimeError):
     pass
 
@@ -81,6 +91,7 @@ SIGNATURES = {
     'b2ins_psd_series_f64': (_I, [_D, _L, _L, _I, _I, _P, _P, _U64, _L, _P, _P, _P]),
     'b2ins_path_rows': (_L, [_P, _L, _D]),
     'b2ins_path_gen_host': (_L, [_P, _P, _L, _D, _D, _D, _D, _P, _I, _L, _P, _P, _P, c_int64_p, _P]),
+    'b2ins_ins_loose_f64': (_I, [ctypes.POINTER(EkfConfig)] + [_P] * 15),
     'b2ins_diag_dfma_rate': (_I, [c_double_p]),
     'b2ins_diag_auto_lanes': (_I, [_L, _I, _I]),
     'b2ins_diag_mc_shape': (_I, [_I, ctypes.POINTER(ctypes.c_int)]),

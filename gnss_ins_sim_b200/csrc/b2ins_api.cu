@@ -15,6 +15,7 @@
 #include "pathgen_host.h"
 #include "psd_kernel.cuh"
 #include "gps_kernel.cuh"
+#include "ekf_kernel.cuh"
 #include "stats_kernel.cuh"
 
 #ifdef B2INS_SINGLE_TU
@@ -757,6 +758,88 @@ int b2ins_mc_plan_run(b2ins_mc_plan* plan, const b2ins_mc_config* cfg, const dou
 
 double* b2ins_mc_plan_err_device(b2ins_mc_plan* plan) { return plan ? plan->d_out + 27 : nullptr; }
 void* b2ins_mc_plan_stream(b2ins_mc_plan* plan) { return plan ? plan->stream : nullptr; }
+
+// ---------------------------------------------------------------- K7 --------
+int b2ins_ins_loose_f64(const b2ins_ekf_config* cfg, const double* ref_gyro, const double* ref_accel,
+                        const double* ref_nav, const double* ref_gps, const int64_t* gps_idx,
+                        const double* gps_vis, double* end_err, double* end_bias, double* consist,
+                        double* dump_att, double* dump_pos, double* dump_vel, double* dump_wb,
+                        double* dump_ab, void* stream) {
+  ARG_CHECK(cfg, "cfg is null");
+  ARG_CHECK(cfg->fs > 0.0, "fs must be positive");
+  ARG_CHECK(cfg->runs >= 0 && cfg->n >= 0 && cfg->m >= 0, "runs, n and m must be non-negative");
+  if (cfg->runs == 0 || cfg->n == 0) return B2INS_OK;
+  ARG_CHECK(cfg->n < (int64_t(1) << 32), "n must be < 2^32");
+  ARG_CHECK(ref_gyro && ref_accel && ref_nav && end_err, "null buffer");
+  ARG_CHECK(cfg->m == 0 || (ref_gps && gps_idx && gps_vis), "m > 0 needs ref_gps, gps_idx and gps_vis");
+  ARG_CHECK(cfg->dump_runs >= 0 && cfg->dump_runs <= cfg->runs, "dump_runs out of range");
+  const int ndump = (dump_att != nullptr) + (dump_pos != nullptr) + (dump_vel != nullptr) + (dump_wb != nullptr) +
+                    (dump_ab != nullptr);
+  ARG_CHECK(ndump == 0 || ndump == 5, "dump_att/pos/vel/wb/ab must be given together");
+  ARG_CHECK(cfg->dump_stride >= 0, "dump_stride must be >= 0");
+  EkfParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = cfg->n;
+  p.runs = cfg->runs;
+  p.run_offset = cfg->run_offset;
+  p.m = cfg->m;
+  p.dt = 1.0 / cfg->fs;
+  p.earth_rot = cfg->earth_rot;
+  p.k0 = static_cast<uint32_t>(cfg->seed);
+  p.k1 = static_cast<uint32_t>(cfg->seed >> 32);
+  int rc = digest_triad(&cfg->gyro_err, nullptr, cfg->fs, &p.gyro);
+  if (rc != B2INS_OK) return rc;
+  rc = digest_triad(&cfg->accel_err, nullptr, cfg->fs, &p.accel);
+  if (rc != B2INS_OK) return rc;
+  p.ref_gyro = ref_gyro;
+  p.ref_accel = ref_accel;
+  p.ref_nav = ref_nav;
+  p.ref_gps = ref_gps;
+  p.gps_idx = gps_idx;
+  p.gps_vis = gps_vis;
+  for (int c = 0; c < 3; ++c) {
+    p.stdp[c] = cfg->gps_stdp[c];
+    p.stdv[c] = cfg->gps_stdv[c];
+    p.p0[c] = cfg->gps_stdp[c] * cfg->gps_stdp[c];
+    p.p0[3 + c] = cfg->gps_stdv[c] * cfg->gps_stdv[c];
+    p.p0[6 + c] = cfg->ini_att_std[c] * cfg->ini_att_std[c];
+    p.p0[9 + c] = cfg->gyro_err.b_drift[c] * cfg->gyro_err.b_drift[c] + cfg->gyro_err.b[c] * cfg->gyro_err.b[c];
+    p.p0[12 + c] = cfg->accel_err.b_drift[c] * cfg->accel_err.b_drift[c] + cfg->accel_err.b[c] * cfg->accel_err.b[c];
+    // the filter's bias model is the generator's: a = 1 - dt/tau, b^2 (white drift: a = 0, b = drift)
+    const bool wg = std::isinf(cfg->gyro_err.b_corr[c]), wa = std::isinf(cfg->accel_err.b_corr[c]);
+    p.ag[c] = wg ? 0.0 : p.gyro.gm_a[c];
+    p.qg[c] = wg ? p.gyro.wd[c] * p.gyro.wd[c] : p.gyro.gm_b[c] * p.gyro.gm_b[c];
+    p.aa[c] = wa ? 0.0 : p.accel.gm_a[c];
+    p.qa[c] = wa ? p.accel.wd[c] * p.accel.wd[c] : p.accel.gm_b[c] * p.accel.gm_b[c];
+    p.arw2dt[c] = cfg->gyro_err.rw[c] * cfg->gyro_err.rw[c] * p.dt;
+    p.vrw2dt[c] = cfg->accel_err.rw[c] * cfg->accel_err.rw[c] * p.dt;
+  }
+  for (int c = 0; c < 9; ++c) p.ini[c] = cfg->ini[c];
+  p.stats_start = cfg->stats_start;
+  p.end_err = end_err;
+  p.end_bias = end_bias;
+  p.consist = consist;
+  p.out_att = dump_att;
+  p.out_pos = dump_pos;
+  p.out_vel = dump_vel;
+  p.out_wb = dump_wb;
+  p.out_ab = dump_ab;
+  p.dump_runs = ndump ? cfg->dump_runs : 0;
+  p.dump_stride = cfg->dump_stride > 1 ? cfg->dump_stride : 1;
+  p.dump_rows = (cfg->n + p.dump_stride - 1) / p.dump_stride;
+  const size_t smem = sizeof(double) * kEkfN * kEkfN * kEkfThreads;
+  static int attr_dev = -1;
+  int dev = 0;
+  CU_CHECK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    CU_CHECK(cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_dev = dev;
+  }
+  const unsigned grid = static_cast<unsigned>((cfg->runs + kEkfThreads - 1) / kEkfThreads);
+  ekf_kernel<<<grid, kEkfThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
 
 // ---------------------------------------------------------------- K3 --------
 int64_t b2ins_error_stats_workspace_bytes(int ncomp) {

@@ -220,14 +220,17 @@ __device__ __forceinline__ double gm_block(double x, double a, double apj, doubl
 }
 
 // Row of sample t in the (possibly decimated) histories; false: the sample is not kept.
-__device__ __forceinline__ bool dump_row(const McParams& p, int64_t t, int64_t* row) {
-  if (p.dump_stride <= 1) {
+__device__ __forceinline__ bool dump_row_generic(int64_t stride, int64_t t, int64_t* row) {
+  if (stride <= 1) {
     *row = t;
     return true;
   }
-  const int64_t q = t / p.dump_stride;
+  const int64_t q = t / stride;
   *row = q;
-  return q * p.dump_stride == t;
+  return q * stride == t;
+}
+__device__ __forceinline__ bool dump_row(const McParams& p, int64_t t, int64_t* row) {
+  return dump_row_generic(p.dump_stride, t, row);
 }
 
 // attitude.euler2quat, 'zyx' (attitude.py:188-205): [yaw, pitch, roll] -> scalar-first quaternion

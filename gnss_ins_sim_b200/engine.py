@@ -389,3 +389,62 @@ def allan(fs, x, n, nseries, inner=1, outer_stride=None, sample_stride=1):
                                    int(outer_stride), int(sample_stride), _ptr(avar), _ptr(tau),
                                    _ptr(ws), _stream()))
     return avar, tau
+
+
+class EkfResult:
+    """Device-side results of one loosely-coupled-filter launch (K7)."""
+
+    def __init__(self):
+        self.end_err = None      # [R,9] att (wrapped), pos (LLA), vel error at the last sample
+        self.end_bias = None     # [R,6] gyro, accel bias estimates at the last sample
+        self.consist = None      # [R,19] NEES sums (pos, vel, att), inside-3-sigma counts [15], epochs
+        self.att = self.pos = self.vel = self.wb = self.ab = None   # [dump_runs,rows,3]
+
+
+def ins_loose(fs, runs, seed, gyro_err, accel_err, gps_err, ini, ref_gyro, ref_accel, ref_nav, ref_gps,
+              gps_idx, gps_vis, run_offset=0, ini_att_std=(0.02, 0.005, 0.005), earth_rot=True,
+              stats_start=0, dump_runs=0, dump_stride=1, out=None):
+    """K7: Monte-Carlo loosely-coupled GNSS/INS filter (the spec: DESIGN.md section 11; csrc/ekf_kernel.cuh).
+    ref_gyro, ref_accel [n,3], ref_nav [n,9], ref_gps [m,6], gps_vis [m]: CUDA f64; gps_idx [m]: CUDA
+    int64 (IMU sample index of every GPS row).  ini: the 9 true initial values (LLA, body velocity, Euler
+    angles).  Asynchronous on the current stream."""
+    _require_cuda()
+    lib = _lib.load()
+    n, m = ref_gyro.shape[0], ref_gps.shape[0]
+    dev = ref_gyro.device
+    assert gps_idx.dtype == torch.int64 and gps_idx.is_cuda and gps_idx.is_contiguous()
+    cfg = _lib.EkfConfig()
+    cfg.fs, cfg.n, cfg.runs, cfg.run_offset, cfg.m = float(fs), int(n), int(runs), int(run_offset), int(m)
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.gyro_err = _lib.sensor_err(gyro_err, 'arw')
+    cfg.accel_err = _lib.sensor_err(accel_err, 'vrw')
+    stdp = np.broadcast_to(np.asarray(gps_err['stdp'], dtype=np.float64), (3,))
+    stdv = np.broadcast_to(np.asarray(gps_err['stdv'], dtype=np.float64), (3,))
+    ini = np.asarray(ini, dtype=np.float64).reshape(-1)
+    for c in range(3):
+        cfg.gps_stdp[c], cfg.gps_stdv[c] = float(stdp[c]), float(stdv[c])
+        cfg.ini_att_std[c] = float(ini_att_std[c])
+    for c in range(9):
+        cfg.ini[c] = float(ini[c])
+    cfg.stats_start, cfg.dump_runs, cfg.dump_stride = int(stats_start), int(dump_runs), int(dump_stride)
+    cfg.earth_rot = int(bool(earth_rot))
+    res = out or EkfResult()
+
+    def buf(cur, shape):
+        if cur is not None and tuple(cur.shape) == tuple(shape):
+            return cur
+        return torch.empty(shape, dtype=torch.float64, device=dev)
+    res.end_err = buf(res.end_err, (runs, 9))
+    res.end_bias = buf(res.end_bias, (runs, 6))
+    res.consist = buf(res.consist, (runs, 19))
+    if dump_runs > 0:
+        rows = -(-n // max(1, int(dump_stride)))
+        res.att, res.pos, res.vel, res.wb, res.ab = (buf(getattr(res, k), (dump_runs, rows, 3))
+                                                     for k in ('att', 'pos', 'vel', 'wb', 'ab'))
+    else:
+        res.att = res.pos = res.vel = res.wb = res.ab = None
+    _lib.check(lib.b2ins_ins_loose_f64(
+        ctypes.byref(cfg), _ptr(ref_gyro), _ptr(ref_accel), _ptr(ref_nav), _ptr(ref_gps),
+        ctypes.c_void_p(gps_idx.data_ptr()), _ptr(gps_vis), _ptr(res.end_err), _ptr(res.end_bias),
+        _ptr(res.consist), _ptr(res.att), _ptr(res.pos), _ptr(res.vel), _ptr(res.wb), _ptr(res.ab), _stream()))
+    return res

@@ -34,6 +34,7 @@ from . import engine, dist, logged
 from .free_integration import FreeIntegration
 from .free_integration_odo import FreeIntegration as FreeIntegrationOdo
 from .allan_analysis import Allan
+from .ins_loose import InsLoose
 
 D2R = math.pi / 180
 R2D = 180 / math.pi
@@ -419,6 +420,8 @@ class Sim(object):
                     self._run_free_integration(i, a)
                 elif isinstance(a, Allan):
                     self._run_allan(i, a)
+                elif isinstance(a, InsLoose):
+                    self._run_ins_loose(i, a)
                 else:
                     self._run_foreign(i, a)
         self.sim_complete = True
@@ -660,6 +663,64 @@ class Sim(object):
         self.data['ad_accel'] = {'%s_%d' % (name, r): a[r] for r in range(R)}
         self.data['ad_gyro'] = {'%s_%d' % (name, r): g[r] for r in range(R)}
 
+    # ---- loosely-coupled GNSS/INS filter (K7) -------------------------------------------------
+    def _ekf_inputs(self):
+        """Device copies of what K7 reads beside the IMU truth: GPS truth rows, their IMU sample
+        indices, visibility."""
+        if getattr(self, '_ekf_dev', None) is None:
+            t = self._traj
+            if self.ref_frame != 0:
+                raise ValueError('ins_loose works in ref_frame 0 (LLA positions, NED velocities)')
+            if not (getattr(self.imu, 'gps', False) and 'ref_gps' in t and self.fs[1] > 0):
+                raise ValueError('ins_loose needs IMU(gps=True), fs = [fs_imu, fs_gps, ...] and a trajectory '
+                                 'with ref_gps / gps_time / gps_visibility')
+            idx = np.rint(np.asarray(t['gps_time']) * self.fs[0]).astype(np.int64)
+            self._ekf_dev = {'ref_gps': engine.to_device(t['ref_gps']),
+                             'gps_idx': torch.from_numpy(np.ascontiguousarray(idx)).cuda(),
+                             'gps_vis': engine.to_device(np.asarray(t['gps_visibility'], dtype=np.float64))}
+        return self._ekf_dev
+
+    def _ekf_launch(self, algo, r0, runs, stats_start=0, dump_runs=0, dump_stride=1):
+        d, e = self._dev, self._ekf_inputs()
+        ini = algo.ini if algo.ini is not None else self._traj.get('ini')
+        if ini is None:
+            raise ValueError('InsLoose needs ini_pos_vel_att (the trajectory carries no initial state)')
+        return engine.ins_loose(self.fs[0], runs, self.seed, self.imu.gyro_err, self.imu.accel_err,
+                                self.imu.gps_err, ini, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
+                                e['ref_gps'], e['gps_idx'], e['gps_vis'], run_offset=self.run_base + r0,
+                                ini_att_std=algo.ini_att_std, earth_rot=algo.earth_rot,
+                                stats_start=stats_start, dump_runs=dump_runs, dump_stride=dump_stride)
+
+    def _run_ins_loose(self, i, algo):
+        """demo_ins_loose.py semantics, all runs of this rank in one K7 launch: end-point errors and their
+        ensemble statistics (as for free integration), bias estimates, the consistency record."""
+        name = self.algo_name(i)
+        lo, hi = self._shard
+        self._mc[i] = {'base': 0, 'end_err': None}
+        err, stats, con, bias = np.zeros((0, 9)), np.zeros((3, 9)), np.zeros((0, 19)), np.zeros((0, 6))
+        if hi > lo:
+            start = int(round(min(30.0, 0.1 * len(self.data['time']) / self.fs[0]) * self.fs[0]))
+            res = self._ekf_launch(algo, lo, hi - lo, stats_start=start)
+            stats = engine.error_stats(res.end_err).cpu().numpy()
+            err, con, bias = res.end_err.cpu().numpy(), res.consist.cpu().numpy(), res.end_bias.cpu().numpy()
+        self._mc[i].update({'end_err': err, 'consist': con, 'end_bias': bias})
+        self.err_stats[name] = dist.combine_local_stats(stats, hi - lo)
+        algo.run_times += self.sim_count
+        for out in ('att_euler', 'pos', 'vel', 'wb', 'ab'):
+            self.data[out] = LazyRuns(self, (i, out), self.sim_count, prefix=name)
+
+    def ekf_consistency(self, algo_index=0):
+        '''
+        The filter's consistency record over this rank's runs (GPS epochs after the settling time,
+        after the update): {'nees': [R,3] mean NEES of the position / velocity / attitude blocks
+        (expected 3 each), 'inside3': [R,15] fraction of epochs with |error| <= 3 sigma per state
+        (p, v, phi, bg, ba), 'epochs': count, 'end_bias': [R,6] bias estimates at the last sample}.
+        '''
+        c = self._mc[algo_index]['consist']
+        ep = np.maximum(c[:, 18:19], 1.0)
+        return {'nees': c[:, 0:3] / ep, 'inside3': c[:, 3:18] / ep, 'epochs': int(c[0, 18]) if len(c) else 0,
+                'end_bias': self._mc[algo_index]['end_bias']}
+
     def _run_foreign(self, i, algo):
         """Reference-style plugin run on the host, sensor data from K1
         (the per-run protocol of InsAlgoMgr.run_algo, ins_algo_manager.py:73-95)."""
@@ -701,6 +762,13 @@ class Sim(object):
         if isinstance(name, tuple):      # algorithm output (algo index, data name)
             ai, out = name
             key = ('nav', ai, blk)
+            if key not in self._cache and isinstance(self.algo[ai], InsLoose):
+                r0 = blk * self.history_block
+                r1 = min(self.sim_count, r0 + self.history_block)
+                res = self._ekf_launch(self.algo[ai], r0, r1 - r0, dump_runs=r1 - r0)
+                self._cache[key] = {'att_euler': res.att.cpu().numpy(), 'pos': res.pos.cpu().numpy(),
+                                    'vel': res.vel.cpu().numpy(), 'wb': res.wb.cpu().numpy(),
+                                    'ab': res.ab.cpu().numpy()}
             if key not in self._cache:
                 algo = self.algo[ai]
                 r0 = blk * self.history_block

@@ -111,6 +111,47 @@ typedef struct b2ins_mc_config {
                              att_euler it holds (ins_sim.py:729-794, attitude.euler2quat :188-205) */
 } b2ins_mc_config;
 
+/* ---- K7: loosely-coupled GNSS/INS filter (BASELINE config 5) ------------------------------------
+ * Replaces demo_algorithms/ins_loose.py:54-138 (InsLoose.ins_loose / prediction / correction) -- which
+ * in the reference is a stub: its prediction() and correction() are `pass`.  The filter here is a
+ * 15-state closed-loop error-state EKF specified in DESIGN.md section 11 (parity with the reference is
+ * unpinnable; the kernel is held to that spec and validated by NEES / 3-sigma tests), fed by the
+ * reference's sensor models: pathgen.acc_gen / gyro_gen (pathgen.py:441-594) and gps_gen (:596-625)
+ * on the same Philox streams as K12 / K6.  ref_frame 0 only (LLA positions, NED velocities). */
+typedef struct {
+  double fs;
+  int64_t n;            /* IMU samples */
+  int64_t runs;
+  int64_t run_offset;   /* global id of local run 0 */
+  int64_t m;            /* GPS samples */
+  uint64_t seed;
+  b2ins_sensor_err gyro_err;
+  b2ins_sensor_err accel_err;
+  double gps_stdp[3];   /* GPS position noise [m]: generator and filter R (imu_model gps_opt 'stdp') */
+  double gps_stdv[3];   /* GPS velocity noise [m/s] */
+  double ini[9];        /* true initial lat, lon [rad], alt [m], body velocity [m/s], yaw, pitch, roll [rad] */
+  double ini_att_std[3];/* 1-sigma of the initial misalignment (N, E, D) [rad]; initial position / velocity
+                           errors are drawn with the GPS sigmas, bias variances start at drift^2 + b^2 */
+  int64_t stats_start;  /* first IMU sample index of the consistency record */
+  int64_t dump_runs;    /* histories for local runs [0, dump_runs) */
+  int32_t dump_stride;  /* keep samples 0, s, 2s, ... (0, 1 = all) */
+  int32_t earth_rot;
+} b2ins_ekf_config;
+
+/* One launch: every run generates its IMU and GPS measurements, filters them and leaves
+ *   end_err   [runs][9]  att (wrapped), pos (LLA), vel error at sample n-1 (as K12's end_err),
+ *   end_bias  [runs][6]  (nullable) gyro and accel bias estimates at n-1,
+ *   consist   [runs][19] (nullable) over the GPS epochs >= stats_start, after the update: sums of the
+ *             position / velocity / attitude block NEES [3], counts of |error_i| <= 3 sigma_i [15], epochs,
+ *   dump_att/pos/vel/wb/ab (each nullable, all or none) [dump_runs][rows][3] histories.
+ * ref_gyro, ref_accel [n][3], ref_nav [n][9] (att, pos LLA, vel NED), ref_gps [m][6],
+ * gps_idx [m] (int64: IMU sample index of every GPS row, ascending), gps_vis [m]: DEVICE pointers. */
+int b2ins_ins_loose_f64(const b2ins_ekf_config* cfg, const double* ref_gyro, const double* ref_accel,
+                        const double* ref_nav, const double* ref_gps, const int64_t* gps_idx,
+                        const double* gps_vis, double* end_err, double* end_bias, double* consist,
+                        double* dump_att, double* dump_pos, double* dump_vel, double* dump_wb,
+                        double* dump_ab, void* stream);
+
 /* ---- housekeeping ------------------------------------------------------ */
 int b2ins_version(void);
 const char* b2ins_last_error(void);
