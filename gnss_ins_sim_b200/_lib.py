@@ -49,7 +49,8 @@ class EkfConfig(ctypes.Structure):
                 ('gps_stdp', ctypes.c_double * 3), ('gps_stdv', ctypes.c_double * 3),
                 ('ini', ctypes.c_double * 9), ('ini_att_std', ctypes.c_double * 3),
                 ('stats_start', ctypes.c_int64), ('dump_runs', ctypes.c_int64),
-                ('dump_stride', ctypes.c_int32), ('earth_rot', ctypes.c_int32)]
+                ('dump_stride', ctypes.c_int32), ('earth_rot', ctypes.c_int32),
+                ('vel_rw', ctypes.c_double), ('att_rw', ctypes.c_double)]
 
 
 class B2insError(RuntimeError):
@@ -85,6 +86,7 @@ SIGNATURES = {
     'b2ins_error_stats_exchange_f64': (_I, [_L, _I, _P, _I, _I, ctypes.POINTER(ctypes.c_uint64), _U64, _P, _P, _P]),
     'b2ins_allan_workspace_bytes': (_L, [_L, _L]),
     'b2ins_allan_f64': (_I, [_D, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P]),
+    'b2ins_allan_mc_f64': (_I, [_D, _L, _L, _P, _P, _SE, _SE, _U64, _L, _P, _P, _P, _P]),
     'b2ins_allan_f64_host': (_I, [_D, _L, _L, _P, _L, _L, _L, _P, _P]),
     'b2ins_psd_series_len': (_I, [_L]),
     'b2ins_psd_workspace_bytes': (_L, [_L, _L]),

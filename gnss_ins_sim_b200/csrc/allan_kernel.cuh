@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "mc_kernel.cuh"   // TriadNoise: the pre-digested error model of the generating front end
 
 namespace b2ins {
 
@@ -571,6 +572,162 @@ __global__ void __launch_bounds__(kAllanFastThreads, 1) allan_stream_kernel(cons
   if (it > 0 && tid < 9) allan_tile_fold(p, prev_series, prev_chunk, red[(it - 1) & 1]);
 }
 
+// ---- K1 fused into level 0: the series is generated in the tile, never written ------------------
+// The Allan experiment (Sim + the Allan plugin) used to materialise every run's noisy gyro / accel
+// series with K1 (48 B per run-sample) and read them back here: config 4 (256 runs x 14.4 M samples x
+// 6 channels) moved 177 GB through HBM twice, in run blocks sized to memory.  This front end replaces
+// the bulk copy of the stream kernel by the generator: a persistent CTA owns whole series (series s =
+// run s / 6, channel s % 6: accel xyz, gyro xyz -- the Philox draw id of the channel's Box-Muller
+// pair), walks its chunks in order and keeps the Gauss-Markov state of the channel in registers, so no
+// segment pre-pass is needed.  Thread i of the first 504 makes samples 10 i .. 10 i + 9 of the tile:
+// pair (t, channel, run) -> (drift drive, white noise), the zero-state response of its ten drives, and
+// an affine scan over the threads (shuffles within a warp, the sixteen warp totals through shared
+// memory) gives every thread the drift at the start of its stretch:
+//     sample = (ref + b) + w z1 + wd z0 + d[t],   d[t+1] = a d[t] + b_gm z0[t]   (pathgen.py:441-594).
+// What leaves the chip at level 0: the decade sums (0.8 B per sample) and nine partials per chunk.
+struct AllanGenParams {
+  int64_t n, run_offset;
+  uint32_t k0, k1;
+  TriadNoise gyro, accel;       // pre-digested error models (no vibration in this path)
+  const double* ref_gyro;       // [n][3]
+  const double* ref_accel;      // [n][3]
+};
+
+constexpr int kGenPer = 10;                              // samples per thread and tile
+constexpr int kGenThreads = kAllanChunk / kGenPer;       // 504 of the 512 threads generate
+
+__global__ void __launch_bounds__(kAllanFastThreads, 1)
+allan_gen_kernel(const __grid_constant__ AllanLevelParams p, const __grid_constant__ AllanGenParams g) {
+  extern __shared__ __align__(128) double smem[];
+  double* in_buf = smem;                                   // [2][kAllanRawLen]
+  double* pad_buf = smem + 2 * kAllanRawLen;               // [2][kAllanPadLen]
+  __shared__ double red[2][kAllanFastWarps][4];
+  __shared__ double wtot[kAllanFastWarps][2];              // (A, E) of every warp's stretch of the tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cc = static_cast<int>(p.chunk_count);
+  int it = 0;
+  int prev_series = 0, prev_chunk = 0;
+  for (int series = blockIdx.x; series < p.nseries; series += gridDim.x) {
+    const int64_t run = series / 6;
+    const int ch = series - static_cast<int>(run) * 6;
+    const int ax = ch % 3;
+    const TriadNoise& e = (ch < 3) ? g.accel : g.gyro;
+    const double* ref = (ch < 3) ? g.ref_accel : g.ref_gyro;
+    const int64_t grun = g.run_offset + run;
+    const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
+    const double a = e.gm_a[ax], bgm = e.gm_b[ax], wd = e.wd[ax], wn = e.w[ax], bias = e.b[ax];
+    double apow[kGenPer + 1];                              // a^q
+    apow[0] = 1.0;
+#pragma unroll
+    for (int q = 1; q <= kGenPer; ++q) apow[q] = apow[q - 1] * a;
+    double carry = 0.0;                                    // d at the first sample of the tile; d[0] = 0
+    for (int chunk = 0; chunk < cc; ++chunk, ++it) {
+      double* in = in_buf + (it & 1) * kAllanRawLen;
+      const int64_t c0 = static_cast<int64_t>(chunk) * kAllanChunk;
+      const int64_t left_in_series = p.len - c0;
+      const int cnt = left_in_series < kAllanChunk ? static_cast<int>(left_in_series) : kAllanChunk;
+      // ---- generate: white part and the zero-state drift response of this thread's stretch ------
+      double mm[kGenPer], rr[kGenPer];
+      double A = 1.0, E = 0.0;
+      if (tid < kGenThreads) {
+        double r = 0.0;
+#pragma unroll
+        for (int q = 0; q < kGenPer; ++q) {
+          const int el = tid * kGenPer + q;
+          rr[q] = r;
+          mm[q] = 0.0;
+          if (el < cnt) {
+            const int64_t t = c0 + el;
+            const Normal2 z = normal_pair(static_cast<uint32_t>(t), static_cast<uint32_t>(ch), run_lo, run_hi,
+                                          g.k0, g.k1);
+            mm[q] = ((ref[t * 3 + ax] + bias) + wn * z.z1) + wd * z.z0;
+            r = fma(a, r, bgm * z.z0);
+            A *= a;
+          }
+        }
+        E = r;
+      }
+      // ---- affine scan over the threads: (A, E) o (A', E') = (A A', A' E + E') -------------------
+      double sA = A, sE = E;                               // inclusive within the warp
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double uA = __shfl_up_sync(0xffffffffu, sA, off);
+        const double uE = __shfl_up_sync(0xffffffffu, sE, off);
+        if (lane >= off) {
+          sE = fma(sA, uE, sE);
+          sA *= uA;
+        }
+      }
+      if (lane == 31) {
+        wtot[warp][0] = sA;
+        wtot[warp][1] = sE;
+      }
+      __syncthreads();                                     // (1) warp totals; everybody is done with tile it-1
+      if (it > 0 && tid < 9) allan_tile_fold(p, prev_series, prev_chunk, red[(it - 1) & 1]);
+      // exclusive prefix of this thread: the warps before it, then the lanes before it
+      double pA = 1.0, pE = 0.0;
+      for (int w = 0; w < warp; ++w) {
+        pE = fma(wtot[w][0], pE, wtot[w][1]);
+        pA *= wtot[w][0];
+      }
+      {
+        const double lA = __shfl_up_sync(0xffffffffu, sA, 1), lE = __shfl_up_sync(0xffffffffu, sE, 1);
+        if (lane > 0) {
+          pE = fma(lA, pE, lE);
+          pA *= lA;
+        }
+      }
+      const double S = fma(pA, carry, pE);                 // drift at the first sample of the stretch
+      // the tile's total, by every thread alike (same operations, same result): the next carry
+      {
+        double tA = 1.0, tE = 0.0;
+#pragma unroll
+        for (int w = 0; w < kAllanFastWarps; ++w) {
+          tE = fma(wtot[w][0], tE, wtot[w][1]);
+          tA *= wtot[w][0];
+        }
+        carry = fma(tA, carry, tE);
+      }
+      if (tid < kGenThreads) {
+#pragma unroll
+        for (int q = 0; q < kGenPer; ++q)
+          in[kAllanLead + tid * kGenPer + q] = mm[q] + fma(apow[q], S, rr[q]);
+      }
+      // halo: the nine samples before the chunk are the tail of the previous tile of this series
+      if (chunk != 0 && tid >= kAllanFastThreads - 9) {
+        const int k = tid - (kAllanFastThreads - 9);       // 0..8 -> elements -9..-1
+        const double* pin = in_buf + ((it - 1) & 1) * kAllanRawLen;
+        in[1 + k] = pin[kAllanLead + kAllanChunk - 9 + k];
+      }
+      __syncthreads();                                     // (2) the raw tile is complete
+      double* pad = pad_buf + (it & 1) * kAllanPadLen + kAllanPadLead;
+      {
+        const double2* in2 = reinterpret_cast<const double2*>(in);
+        double2* pad2 = reinterpret_cast<double2*>(pad);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int u = tid + q * kAllanFastThreads;
+          if (u < (kAllanLead + kAllanChunk) / 2) {
+            const int ue = u - kAllanLead / 2;
+            pad2[ue >= 0 ? ue + ue / 24 : ue - 1] = in2[u];
+          }
+        }
+      }
+      __syncthreads();                                     // (3) X's padded copy is complete
+      double acc[4];
+      if (static_cast<int64_t>(chunk + 1) * kAllanChunk <= p.len)
+        allan_tile_compute<false, false>(p, series, chunk, in, pad, 0.0, acc);
+      else
+        allan_tile_compute<false, true>(p, series, chunk, in, pad, 0.0, acc);
+      allan_tile_reduce(acc, red[it & 1]);
+      prev_series = series;
+      prev_chunk = chunk;
+    }
+  }
+  __syncthreads();
+  if (it > 0 && tid < 9) allan_tile_fold(p, prev_series, prev_chunk, red[(it - 1) & 1]);
+}
+
 struct AllanFinalParams {
   int64_t nseries;
   int ntau;
@@ -717,9 +874,11 @@ inline int64_t allan_workspace_bytes(int64_t n, int64_t nseries) {
 }
 
 // returns 0 on success
+// gen != nullptr: level 0 is generated on the fly (allan_gen_kernel; x is not read)
 inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, int64_t inner,
                         int64_t outer_stride, int64_t sample_stride, const int64_t* mult, int ntau,
-                        double* avar, double* tau, void* workspace, int sms, cudaStream_t s) {
+                        double* avar, double* tau, void* workspace, int sms, cudaStream_t s,
+                        const AllanGenParams* gen = nullptr) {
   AllanFinalParams fp;
   std::memset(&fp, 0, sizeof(fp));
   fp.nseries = nseries;
@@ -753,6 +912,8 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
   const size_t smem = (kAllanChunk + kAllanHalo + 1 + 16) * sizeof(double);
   const size_t smem_full = (kAllanRawLen + kAllanPadLen) * sizeof(double);
   const size_t smem_stream = (kAllanStages * kAllanRawLen + 2 * kAllanPadLen) * sizeof(double);
+  const size_t smem_gen = (2 * kAllanRawLen + 2 * kAllanPadLen) * sizeof(double);
+  if (gen && n <= kAllanChunk) return 5;   // short series: the caller materialises them
   // function attributes are per device: remember which devices have them
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -769,7 +930,9 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
         cudaFuncSetAttribute(allan_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem_stream)) != cudaSuccess ||
         cudaFuncSetAttribute(allan_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_stream)) != cudaSuccess)
+                             static_cast<int>(smem_stream)) != cudaSuccess ||
+        cudaFuncSetAttribute(allan_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_gen)) != cudaSuccess)
       return 2;
     // both kernels stage everything through shared memory: ask for the largest carve-out so that
     // two (fast kernel) / five (tail kernel) CTAs are resident per SM
@@ -830,7 +993,13 @@ inline int allan_launch(double fs, int64_t n, int64_t nseries, const double* x, 
     const bool aligned = lp.level0 ? (inner == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                                       (outer_stride & 1) == 0)
                                    : (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
-    if (contiguous && aligned) {
+    if (lp.level0 && gen) {
+      // the generator front end: persistent CTAs own whole series
+      lp.chunk_first = 0;
+      lp.chunk_count = lp.chunks;
+      const int64_t grid = nseries < sms ? nseries : sms;
+      allan_gen_kernel<<<static_cast<unsigned>(grid), kAllanFastThreads, smem_gen, s>>>(lp, *gen);
+    } else if (contiguous && aligned) {
       // persistent kernel, every chunk of every series (the ragged last one is masked)
       lp.chunk_first = 0;
       lp.chunk_count = lp.chunks;

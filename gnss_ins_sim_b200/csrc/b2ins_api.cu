@@ -815,6 +815,9 @@ int b2ins_ins_loose_f64(const b2ins_ekf_config* cfg, const double* ref_gyro, con
     p.vrw2dt[c] = cfg->accel_err.rw[c] * cfg->accel_err.rw[c] * p.dt;
   }
   for (int c = 0; c < 9; ++c) p.ini[c] = cfg->ini[c];
+  ARG_CHECK(cfg->vel_rw >= 0.0 && cfg->att_rw >= 0.0, "vel_rw and att_rw must be >= 0");
+  p.qv_extra = cfg->vel_rw * cfg->vel_rw * p.dt;
+  p.qphi_extra = cfg->att_rw * cfg->att_rw * p.dt;
   p.stats_start = cfg->stats_start;
   p.end_err = end_err;
   p.end_bias = end_bias;
@@ -952,6 +955,37 @@ int b2ins_allan_f64(double fs, int64_t n, int64_t nseries, const double* x, int6
   const int rc = allan_launch(fs, n, nseries, x, inner, outer_stride, sample_stride, mult, ntau,
                               avar, tau, workspace, sm_count(), s);
   if (rc != 0) return fail(B2INS_ERR_CUDA, "allan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  CU_CHECK(cudaGetLastError());
+  return B2INS_OK;
+}
+
+int b2ins_allan_mc_f64(double fs, int64_t n, int64_t runs, const double* ref_gyro,
+                       const double* ref_accel, const b2ins_sensor_err* gyro_err,
+                       const b2ins_sensor_err* accel_err, uint64_t seed, int64_t run_offset,
+                       double* avar, double* tau, void* workspace, void* stream) {
+  ARG_CHECK(fs > 0.0 && n >= 0 && runs >= 0, "bad fs/n/runs");
+  int64_t mult[128];
+  const int ntau = b2ins_allan_num_tau(n, fs, mult, 128);
+  if (ntau == 0 || runs == 0) return B2INS_OK;
+  ARG_CHECK(ntau <= 128, "too many tau");
+  ARG_CHECK(n > kAllanChunk, "the fused Allan path needs more than %d samples per series", kAllanChunk);
+  ARG_CHECK(n < (int64_t(1) << 32), "n must be < 2^32");
+  ARG_CHECK(ref_gyro && ref_accel && gyro_err && accel_err && avar && tau && workspace, "null buffer");
+  AllanGenParams g;
+  std::memset(&g, 0, sizeof(g));
+  g.n = n;
+  g.run_offset = run_offset;
+  g.k0 = static_cast<uint32_t>(seed);
+  g.k1 = static_cast<uint32_t>(seed >> 32);
+  int rc = digest_triad(gyro_err, nullptr, fs, &g.gyro);
+  if (rc != B2INS_OK) return rc;
+  rc = digest_triad(accel_err, nullptr, fs, &g.accel);
+  if (rc != B2INS_OK) return rc;
+  g.ref_gyro = ref_gyro;
+  g.ref_accel = ref_accel;
+  rc = allan_launch(fs, n, runs * 6, nullptr, 1, n, 1, mult, ntau, avar, tau, workspace, sm_count(),
+                    static_cast<cudaStream_t>(stream), &g);
+  if (rc != 0) return fail(B2INS_ERR_CUDA, "allan launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }

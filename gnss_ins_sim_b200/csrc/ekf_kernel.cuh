@@ -42,6 +42,7 @@ struct EkfParams {
   double ini[9];                   // true initial LLA, body velocity, Euler angles
   double ag[3], qg[3], aa[3], qa[3];   // bias model: a and b^2 per axis
   double arw2dt[3], vrw2dt[3];
+  double qv_extra, qphi_extra;     // model-mismatch random walks: vel_rw^2 dt, att_rw^2 dt
   int64_t stats_start;
   double* end_err;                 // [runs][9]
   double* end_bias;                // [runs][6]
@@ -374,6 +375,8 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
         }
 #pragma unroll
       for (int c3 = 0; c3 < 3; ++c3) {
+        P(3 + c3, 3 + c3) += p.qv_extra;
+        P(6 + c3, 6 + c3) += p.qphi_extra;
         P(9 + c3, 9 + c3) += p.qg[c3];
         P(12 + c3, 12 + c3) += p.qa[c3];
       }

@@ -391,6 +391,27 @@ def allan(fs, x, n, nseries, inner=1, outer_stride=None, sample_stride=1):
     return avar, tau
 
 
+def allan_mc(fs, runs, ref_gyro, ref_accel, gyro_err, accel_err, seed, run_offset=0):
+    """K1 fused into K4: Allan variance of `runs` Monte-Carlo runs x 6 channels whose series are
+    generated inside the tau-binning kernel (never written).  ref_gyro, ref_accel: CUDA f64 [n,3].
+    Returns avar [runs, 6, ntau] (channels: accel x y z, gyro x y z) and tau [ntau] (CUDA)."""
+    _require_cuda()
+    lib = _lib.load()
+    n = ref_gyro.shape[0]
+    ntau = len(allan_num_tau(n, fs))
+    avar = torch.zeros((runs, 6, ntau), dtype=torch.float64, device=ref_gyro.device)
+    tau = torch.zeros((ntau,), dtype=torch.float64, device=ref_gyro.device)
+    if ntau == 0 or runs == 0:
+        return avar, tau
+    ws = torch.empty(lib.b2ins_allan_workspace_bytes(n, runs * 6) // 8 + 1, dtype=torch.float64,
+                     device=ref_gyro.device)
+    ge, ae = _lib.sensor_err(gyro_err, 'arw'), _lib.sensor_err(accel_err, 'vrw')
+    _lib.check(lib.b2ins_allan_mc_f64(float(fs), int(n), int(runs), _ptr(ref_gyro), _ptr(ref_accel),
+                                      ctypes.byref(ge), ctypes.byref(ae), int(seed), int(run_offset),
+                                      _ptr(avar), _ptr(tau), _ptr(ws), _stream()))
+    return avar, tau
+
+
 class EkfResult:
     """Device-side results of one loosely-coupled-filter launch (K7)."""
 
@@ -403,7 +424,7 @@ class EkfResult:
 
 def ins_loose(fs, runs, seed, gyro_err, accel_err, gps_err, ini, ref_gyro, ref_accel, ref_nav, ref_gps,
               gps_idx, gps_vis, run_offset=0, ini_att_std=(0.02, 0.005, 0.005), earth_rot=True,
-              stats_start=0, dump_runs=0, dump_stride=1, out=None):
+              stats_start=0, dump_runs=0, dump_stride=1, out=None, vel_rw=0.02, att_rw=0.0):
     """K7: Monte-Carlo loosely-coupled GNSS/INS filter (the spec: DESIGN.md section 11; csrc/ekf_kernel.cuh).
     ref_gyro, ref_accel [n,3], ref_nav [n,9], ref_gps [m,6], gps_vis [m]: CUDA f64; gps_idx [m]: CUDA
     int64 (IMU sample index of every GPS row).  ini: the 9 true initial values (LLA, body velocity, Euler
@@ -428,6 +449,7 @@ def ins_loose(fs, runs, seed, gyro_err, accel_err, gps_err, ini, ref_gyro, ref_a
         cfg.ini[c] = float(ini[c])
     cfg.stats_start, cfg.dump_runs, cfg.dump_stride = int(stats_start), int(dump_runs), int(dump_stride)
     cfg.earth_rot = int(bool(earth_rot))
+    cfg.vel_rw, cfg.att_rw = float(vel_rw), float(att_rw)
     res = out or EkfResult()
 
     def buf(cur, shape):

@@ -22,7 +22,8 @@ class InsLoose(object):
     Loosely coupled INS algorithm (device-backed, Monte-Carlo form).
     '''
 
-    def __init__(self, ini_pos_vel_att=None, ini_att_std=(0.02, 0.005, 0.005), earth_rot=True):
+    def __init__(self, ini_pos_vel_att=None, ini_att_std=(0.02, 0.005, 0.005), earth_rot=True,
+                 vel_model_std=0.02, att_model_std=0.0):
         '''
         Args:
             ini_pos_vel_att: (9,) true initial LLA [rad, rad, m], body velocity, ZYX Euler angles; None:
@@ -30,6 +31,10 @@ class InsLoose(object):
                 this state plus a draw from the initial covariance.
             ini_att_std: 1-sigma of the initial misalignment about N, E, D [rad].
             earth_rot: consider the Earth rotation in the mechanization.
+            vel_model_std, att_model_std: extra velocity [m/s/sqrt(s)] and misalignment [rad/sqrt(s)]
+                random walks of the filter model.  The reference's truth generator and its first-order
+                mechanization disagree slightly (noise-free free integration of motion_def-ins.csv ends
+                0.37 m/s off); 0.02 m/s/sqrt(s) covers that and keeps the filter consistent.
         '''
         self.input = ['fs', 'gyro', 'accel', 'time', 'gps_time', 'gps']   # ins_loose.py:31
         self.output = ['pos', 'vel', 'att_euler', 'wb', 'ab']             # ins_loose.py:32
@@ -38,6 +43,7 @@ class InsLoose(object):
         self.ini = None if ini_pos_vel_att is None else np.asarray(ini_pos_vel_att, dtype=np.float64).reshape(-1)[:9]
         self.ini_att_std = tuple(float(v) for v in ini_att_std)
         self.earth_rot = bool(earth_rot)
+        self.vel_model_std, self.att_model_std = float(vel_model_std), float(att_model_std)
         self.run_times = 0
 
     def run(self, set_of_input):

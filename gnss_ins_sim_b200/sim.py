@@ -632,6 +632,8 @@ class Sim(object):
         R = self.sim_count
         lo, hi = self._shard
         n = self._traj['ref_gyro'].shape[0]
+        if self._vib_acc is None and self._vib_gyro is None and n > 5040 and os.environ.get('B2INS_ALLAN_FUSED', '1') != '0':
+            return self._run_allan_fused(i, name, R, lo, hi, n)
         # runs per block: K1 materialises 48 B and K4 needs ~2 B of workspace per run-sample;
         # use up to a third of the free device memory
         if torch.cuda.is_available():    # free on the device + cached by torch's allocator but unused
@@ -689,7 +691,8 @@ class Sim(object):
                                 self.imu.gps_err, ini, d['ref_gyro'], d['ref_accel'], d['ref_nav'],
                                 e['ref_gps'], e['gps_idx'], e['gps_vis'], run_offset=self.run_base + r0,
                                 ini_att_std=algo.ini_att_std, earth_rot=algo.earth_rot,
-                                stats_start=stats_start, dump_runs=dump_runs, dump_stride=dump_stride)
+                                stats_start=stats_start, dump_runs=dump_runs, dump_stride=dump_stride,
+                                vel_rw=algo.vel_model_std, att_rw=algo.att_model_std)
 
     def _run_ins_loose(self, i, algo):
         """demo_ins_loose.py semantics, all runs of this rank in one K7 launch: end-point errors and their
@@ -720,6 +723,32 @@ class Sim(object):
         ep = np.maximum(c[:, 18:19], 1.0)
         return {'nees': c[:, 0:3] / ep, 'inside3': c[:, 3:18] / ep, 'epochs': int(c[0, 18]) if len(c) else 0,
                 'end_bias': self._mc[algo_index]['end_bias']}
+
+    def _run_allan_fused(self, i, name, R, lo, hi, n):
+        """The Allan experiment without the series: K1 fused into K4's first level (engine.allan_mc).
+        Used when no vibration model is set and the series is longer than one chunk; the only device
+        memory is the decade-sum workspace (about 2 B per run-sample), so run blocks are rarely needed."""
+        d = self._dev
+        tau_all = engine.allan_taus(n, self.fs[0])
+        ntau = len(tau_all)
+        if torch.cuda.is_available():
+            free_b = (torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated())
+        else:
+            free_b = 2 ** 31
+        block = max(1, min(max(hi - lo, 1), int(free_b / 2 // (n * 6 * 2)) or 1))
+        parts = []
+        for r0 in range(lo, hi, block):
+            r1 = min(hi, r0 + block)
+            avar, _ = engine.allan_mc(self.fs[0], r1 - r0, d['ref_gyro'], d['ref_accel'], self.imu.gyro_err,
+                                      self.imu.accel_err, self.seed, run_offset=self.run_base + r0)
+            parts.append(torch.sqrt(avar).permute(0, 2, 1).contiguous().cpu().numpy())     # [r, ntau, 6]
+        both = np.concatenate(parts) if parts else np.zeros((0, ntau, 6))
+        if dist.world() > 1:
+            both = dist.gather_rows(torch.from_numpy(np.ascontiguousarray(both.reshape(hi - lo, -1))), R)
+            both = both.reshape(R, ntau, 6)
+        self.data['algo_time'] = {'%s_%d' % (name, r): tau_all for r in range(R)}
+        self.data['ad_accel'] = {'%s_%d' % (name, r): both[r, :, 0:3] for r in range(R)}
+        self.data['ad_gyro'] = {'%s_%d' % (name, r): both[r, :, 3:6] for r in range(R)}
 
     def _run_foreign(self, i, algo):
         """Reference-style plugin run on the host, sensor data from K1

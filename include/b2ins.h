@@ -111,6 +111,18 @@ typedef struct b2ins_mc_config {
                              att_euler it holds (ins_sim.py:729-794, attitude.euler2quat :188-205) */
 } b2ins_mc_config;
 
+/* ---- K1 + K4 fused: the Allan experiment without the series ------------------------------------
+ * Replaces, for a whole Monte-Carlo Allan experiment, pathgen.acc_gen / gyro_gen (pathgen.py:441-594)
+ * followed by allan.allan_var (allan.py:18-59) per run and channel (Allan.run, allan_analysis.py:29-49):
+ * every (run, channel) series is generated tile by tile inside the tau-binning kernel and never
+ * written.  Series s = run * 6 + channel (accel x y z, gyro x y z).  No vibration models here (the
+ * caller materialises the series with b2ins_imu_noise_f64 when env is set); n must exceed 5040.
+ *   avar [runs * 6][ntau], tau [ntau]; workspace: b2ins_allan_workspace_bytes(n, runs * 6). */
+int b2ins_allan_mc_f64(double fs, int64_t n, int64_t runs, const double* ref_gyro,
+                       const double* ref_accel, const b2ins_sensor_err* gyro_err,
+                       const b2ins_sensor_err* accel_err, uint64_t seed, int64_t run_offset,
+                       double* avar, double* tau, void* workspace, void* stream);
+
 /* ---- K7: loosely-coupled GNSS/INS filter (BASELINE config 5) ------------------------------------
  * Replaces demo_algorithms/ins_loose.py:54-138 (InsLoose.ins_loose / prediction / correction) -- which
  * in the reference is a stub: its prediction() and correction() are `pass`.  The filter here is a
@@ -136,6 +148,11 @@ typedef struct {
   int64_t dump_runs;    /* histories for local runs [0, dump_runs) */
   int32_t dump_stride;  /* keep samples 0, s, 2s, ... (0, 1 = all) */
   int32_t earth_rot;
+  double vel_rw;        /* extra velocity random walk of the filter model [m/s/sqrt(s)]: covers the
+                           mismatch between the reference's truth generator and its own first-order
+                           mechanization (noise-free free integration of motion_def-ins.csv drifts by
+                           0.37 m/s); 0.02 keeps the filter consistent on that trajectory */
+  double att_rw;        /* extra misalignment random walk [rad/sqrt(s)] */
 } b2ins_ekf_config;
 
 /* One launch: every run generates its IMU and GPS measurements, filters them and leaves

@@ -21,7 +21,10 @@ The filter: 15 error states, closed loop.
                       dbg' = -dbg / tau_g - q_g,   dba' = -dba / tau_a - q_a    (first-order Gauss-Markov)
                   Phi = I + F dt;  Q: C diag(vrw^2) C^T dt, C diag(arw^2) C^T dt, and the bias drives
                   exactly as the generator draws them (b^2 = drift^2 (1 - exp(-2 dt / tau)),
-                  a = 1 - dt / tau, pathgen.py:583-586).
+                  a = 1 - dt / tau, pathgen.py:583-586); plus vel_rw^2 dt I and att_rw^2 dt I, the
+                  model-mismatch random walks (the reference's truth generator and its first-order
+                  mechanization disagree: noise-free free integration of motion_def-ins.csv drifts by
+                  0.37 m/s; the product's default vel_rw = 0.02 m/s/sqrt(s) keeps the filter consistent).
   measurement     every GPS sample (visibility 1): z = [p_hat - p_gps (metres NED); v_hat - v_gps],
                   H = [I 0 0 0 0; 0 I 0 0 0], R = diag(stdp^2, stdv^2): six scalar updates, then the
                   nominal state is corrected (p, v, biases subtract; C <- (I + [phi x]) C_hat; Euler
@@ -96,7 +99,7 @@ def initial_errors(run_ids, seed, p0):
 
 def ins_loose(fs, ref_gyro, ref_accel, ref_nav, ref_gps, gps_idx, gps_vis, gyro_err, accel_err, gps_err,
               seed, run_ids, ini, ini_att_std=(0.02, 0.005, 0.005), earth_rot=True, stats_start=0,
-              want_hist=False):
+              want_hist=False, vel_rw=0.0, att_rw=0.0):
     """Monte-Carlo loosely-coupled filter, runs vectorised.
     ref_nav [n, 9] = true att, pos (LLA), vel (NED); ref_gps [m, 6]; gps_idx [m] IMU sample index of
     every GPS row; ini (9,) true initial LLA, body velocity, Euler angles.
@@ -219,8 +222,8 @@ def ins_loose(fs, ref_gyro, ref_accel, ref_nav, ref_gps, gps_idx, gps_vis, gyro_
         Phi[:, 9:12, 9:12] = np.diag(a_g)
         Phi[:, 12:15, 12:15] = np.diag(a_a)
         Q = np.zeros((R, 15, 15))
-        Q[:, 3:6, 3:6] = np.einsum('rij,j,rkj->rik', c_bn, vrw2, c_bn) * dt
-        Q[:, 6:9, 6:9] = np.einsum('rij,j,rkj->rik', c_bn, arw2, c_bn) * dt
+        Q[:, 3:6, 3:6] = np.einsum('rij,j,rkj->rik', c_bn, vrw2, c_bn) * dt + np.eye(3) * (vel_rw * vel_rw * dt)
+        Q[:, 6:9, 6:9] = np.einsum('rij,j,rkj->rik', c_bn, arw2, c_bn) * dt + np.eye(3) * (att_rw * att_rw * dt)
         Q[:, 9:12, 9:12] = np.diag(b_g ** 2)
         Q[:, 12:15, 12:15] = np.diag(b_a ** 2)
         P = np.einsum('rij,rjk,rlk->ril', Phi, P, Phi) + Q

@@ -222,3 +222,52 @@ def test_gps_streams_follow_run_base(gpu):
     ga, gb = a.get_data(['gps'])[0], b.get_data(['gps'])[0]
     assert np.array_equal(ga[2], gb[0]) and np.array_equal(ga[3], gb[1])
     assert not np.array_equal(ga[0], gb[0])
+
+
+@pytest.mark.parametrize('n', [5041, 20000, 50400, 123457])
+def test_fused_allan_equals_materialised_series(gpu, n):
+    """K1 fused into K4 (the series generated inside the tau-binning kernel, never written) against
+    K1 -> K4 on the materialised series of the same runs: same Philox draws, same Allan variances
+    (the Gauss-Markov scan is associated differently: last-bit differences only)."""
+    from gnss_ins_sim_b200 import engine, imu_model
+    rng = np.random.default_rng(n)
+    ref_gyro = engine.to_device(0.01 * rng.standard_normal((n, 3)))
+    ref_accel = engine.to_device(np.array([0.3, -0.2, -9.8]) + 0.01 * rng.standard_normal((n, 3)))
+    for accuracy in ('low-accuracy', {'gyro_b': np.array([10.0, -5.0, 2.0]), 'gyro_arw': np.array([0.3, 0.2, 0.1]),
+                                      'gyro_b_stability': np.array([8.0, 6.0, 4.0]),
+                                      'accel_b': np.array([1e-3, 0.0, -2e-3]), 'accel_vrw': np.array([0.04, 0.03, 0.05]),
+                                      'accel_b_stability': np.array([1e-4, 2e-4, 5e-5]),
+                                      'gyro_b_corr': np.array([50.0, np.inf, 300.0])}):
+        imu = imu_model.IMU(accuracy=accuracy, axis=6, gps=False)
+        R, r0, seed = 7, 40, 99
+        avar, tau = engine.allan_mc(200.0, R, ref_gyro, ref_accel, imu.gyro_err, imu.accel_err, seed, run_offset=r0)
+        gyro, accel = engine.imu_noise(200.0, R, ref_gyro, ref_accel, imu.gyro_err, imu.accel_err, seed,
+                                       run_offset=r0, layout=engine.LAYOUT_CHANNEL_MAJOR)
+        av_a, tau_a = engine.allan(200.0, accel, n, R * 3)
+        av_g, _ = engine.allan(200.0, gyro, n, R * 3)
+        assert np.array_equal(tau.cpu().numpy(), tau_a.cpu().numpy())
+        ref = np.concatenate([av_a.cpu().numpy().reshape(R, 3, -1), av_g.cpu().numpy().reshape(R, 3, -1)], axis=1)
+        got = avar.cpu().numpy()
+        assert got.shape == ref.shape and np.all(ref > 0)
+        assert np.abs(got / ref - 1.0).max() < 1e-9, (n, np.abs(got / ref - 1.0).max())
+
+
+def test_allan_experiment_takes_the_fused_path_and_agrees(gpu, monkeypatch):
+    """Sim + Allan: the default (fused) experiment equals the materialising one (B2INS_ALLAN_FUSED=0)."""
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.allan_analysis import Allan
+    n = 30000
+    z = np.zeros((n, 3))
+    traj = {'ref_pos': z, 'ref_vel': z, 'ref_att': z, 'ref_accel': np.tile([0.0, 0.0, -9.8], (n, 1)), 'ref_gyro': z}
+    out = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('B2INS_ALLAN_FUSED', fused)
+        sim = Sim([100.0, 0.0, 0.0], traj, ref_frame=1, imu=imu_model.IMU('low-accuracy', axis=6, gps=False),
+                  algorithm=Allan(), seed=21)
+        sim.run(5)
+        out[fused] = (np.stack([sim.get_data(['ad_gyro'])[0]['algo0_%d' % r] for r in range(5)]),
+                      np.stack([sim.get_data(['ad_accel'])[0]['algo0_%d' % r] for r in range(5)]),
+                      sim.get_data(['algo_time'])[0]['algo0_0'])
+    for a, b in zip(out['1'], out['0']):
+        assert a.shape == b.shape and np.abs(a / b - 1.0).max() < 1e-9
