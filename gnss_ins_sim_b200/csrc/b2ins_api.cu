@@ -434,7 +434,7 @@ int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gy
   double* scratch = nullptr;
   if (nseg > 1) {
     int64_t len = (n + nseg - 1) / nseg;
-    len = (len + kNoiseThreads - 1) / kNoiseThreads * kNoiseThreads;   // whole tiles per segment
+    len = (len + kNoiseTile - 1) / kNoiseTile * kNoiseTile;   // whole tiles per segment
     p.seg_len = len;
     p.nseg = static_cast<int>((n + len - 1) / len);
     CU_CHECK(cudaMallocAsync(&scratch, sizeof(double) * runs * p.nseg * 12, s));
@@ -451,7 +451,7 @@ int b2ins_imu_noise_f64(double fs, int64_t runs, int64_t n, const double* ref_gy
         if (need > static_cast<double>(keep)) keep = need >= static_cast<double>(len) ? len : static_cast<int64_t>(need);
       }
     }
-    keep = (keep + kNoiseThreads - 1) / kNoiseThreads * kNoiseThreads;
+    keep = (keep + kNoiseTile - 1) / kNoiseTile * kNoiseTile;
     p.pass1_len = keep < len ? keep : len;
     p.pass = 1;
     if (p.nseg > 1)
@@ -1026,7 +1026,8 @@ int b2ins_psd_series_len(int64_t n) { return n > 0 ? psd_series_len(n) : 0; }
 int64_t b2ins_psd_workspace_bytes(int64_t n, int64_t runs) {
   if (n <= 0 || runs <= 0) return 16;
   const int64_t L = psd_series_len(n) / 2 + 1;
-  return runs * 3 * L * 2 * static_cast<int64_t>(sizeof(double)) + 16;
+  // (A, B) of every bin, then the transform of the chirp for the Bluestein lengths (<= 8192 complex)
+  return runs * 3 * L * 2 * static_cast<int64_t>(sizeof(double)) + 8192 * 16 + 64;
 }
 
 int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int table_len,
@@ -1056,8 +1057,42 @@ int b2ins_psd_series_f64(double fs, int64_t n, int64_t runs, int sensor, int tab
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 g1((p.L + kPsdThreads - 1) / kPsdThreads, static_cast<unsigned>(runs * 3));
   psd_phase_kernel<<<g1, kPsdThreads, 0, s>>>(p);
-  dim3 g2((p.N + kPsdThreads - 1) / kPsdThreads, static_cast<unsigned>(runs * 3));
-  psd_synth_kernel<<<g2, kPsdThreads, 0, s>>>(p);
+  int bluestein = 0;
+  static const bool no_fft = std::getenv("B2INS_PSD_DIRECT") != nullptr;     // tools: A/B the two paths
+  const int P = no_fft ? 0 : psd_fft_plan(p.N, &bluestein);
+  if (P == 0) {      // lengths without an FFT path: the O(N L) cosine synthesis
+    dim3 g2((p.N + kPsdThreads - 1) / kPsdThreads, static_cast<unsigned>(runs * 3));
+    psd_synth_kernel<<<g2, kPsdThreads, 0, s>>>(p);
+    CU_CHECK(cudaGetLastError());
+    return B2INS_OK;
+  }
+  PsdFftParams f;
+  f.nseries = runs * 3;
+  f.N = p.N;
+  f.L = p.L;
+  f.M = p.N / 2;
+  f.P = P;
+  f.logP = 0;
+  while ((1 << f.logP) < P) ++f.logP;
+  f.bluestein = bluestein;
+  f.ab = p.ab;
+  // the chirp transform sits behind the (A, B) block, 16-byte aligned
+  uintptr_t tail = reinterpret_cast<uintptr_t>(p.ab + runs * 3 * static_cast<int64_t>(p.L) * 2);
+  tail = (tail + 15) & ~static_cast<uintptr_t>(15);
+  f.bhat = reinterpret_cast<double2*>(tail);
+  f.series = series;
+  const size_t smem = static_cast<size_t>(P) * 16 + static_cast<size_t>(P / 2) * 16;
+  static int attr_dev = -1;
+  int dev = 0;
+  CU_CHECK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    CU_CHECK(cudaFuncSetAttribute(psd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24));
+    CU_CHECK(cudaFuncSetAttribute(psd_chirp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24));
+    attr_dev = dev;
+  }
+  if (bluestein) psd_chirp_kernel<<<1, kFftThreads, smem, s>>>(f);
+  const int64_t grid = f.nseries < 2 * sm_count() ? f.nseries : 2 * sm_count();
+  psd_fft_kernel<<<static_cast<unsigned>(grid), kFftThreads, smem, s>>>(f);
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }

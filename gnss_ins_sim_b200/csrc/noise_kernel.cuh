@@ -1,16 +1,22 @@
 // K1: IMU sensor-error generator, materialised -- pathgen.acc_gen / gyro_gen / bias_drift
-// (pathgen.py:441-594).  Time-parallel: one CTA per run walks the samples in tiles of
-// kNoiseThreads; thread i draws the normals of sample tile0+i (Philox4x32-10, Box-Muller),
-// the first-order Gauss-Markov drift d[t+1] = a d[t] + b z[t] is an affine block scan
-// (warp shuffles + one shared-memory hop) with the carry kept across tiles, and the
-// measurements are written with the caller's strides.
+// (pathgen.py:441-594).  One CTA per (run, time segment) walks the samples in tiles of kNoiseTile;
+// thread i makes the kNoisePer consecutive samples i kNoisePer .. of the tile, one after the other:
+// six Box-Muller pairs per sample (Philox4x32-10), the measurement without the drift at the start of
+// its stretch staged in shared memory, the Gauss-Markov recurrence d[t+1] = a d[t] + b z[t] run
+// serially inside the stretch (one FMA per sample and channel).  What the stretches owe each other is
+// an affine scan over the 128 threads of a tile -- shuffles within a warp, four warp totals through
+// shared memory: ONE exchange per kNoisePer samples instead of one per sample -- after which every
+// thread adds a^q S to its samples and the tile leaves shared memory in the caller's layout with
+// coalesced stores.
 #pragma once
 #include "mc_kernel.cuh"
 
 namespace b2ins {
 
-constexpr int kNoiseThreads = 256;
+constexpr int kNoiseThreads = 128;
 constexpr int kNoiseWarps = kNoiseThreads / 32;
+constexpr int kNoisePer = 7;                               // consecutive samples per thread and tile
+constexpr int kNoiseTile = kNoiseThreads * kNoisePer;      // 896 samples per tile (the staged tile fits 48 KB)
 
 struct NoiseParams {
   int64_t n, runs, run_offset;
@@ -38,10 +44,9 @@ struct NoiseParams {
   double* seg_end;
 };
 
-__global__ void __launch_bounds__(kNoiseThreads, 2) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
-  __shared__ double apow[6][kNoiseThreads + 1];
-  __shared__ double sh_w[6][kNoiseWarps];     // inclusive warp totals of the six channels
-  __shared__ double sh_pre[6][kNoiseWarps + 1];   // zero-state value at the end of warps < w; [..][8] = tile
+__global__ void __launch_bounds__(kNoiseThreads, 3) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
+  __shared__ double stage[2][kNoiseTile * 3];     // accel, gyro of the tile, [sample][axis]
+  __shared__ double wtot[6][kNoiseWarps][2];      // (A, E) of every warp's stretch, per channel
   const int segs = (p.pass == 1) ? p.nseg - 1 : p.nseg;
   const int64_t run = blockIdx.x / segs;
   const int seg = static_cast<int>(blockIdx.x % segs);
@@ -49,13 +54,12 @@ __global__ void __launch_bounds__(kNoiseThreads, 2) imu_noise_kernel(const __gri
   const int64_t seg_lo = (p.pass == 1) ? seg_hi - p.pass1_len : seg * p.seg_len;
   const int64_t grun = p.run_offset + run;
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
-  const int i = threadIdx.x;
-  for (int k = threadIdx.x; k <= kNoiseThreads; k += kNoiseThreads) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a[6], bgm[6], wdc[6];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      apow[c][k] = pow(p.accel.gm_a[c], static_cast<double>(k));
-      apow[3 + c][k] = pow(p.gyro.gm_a[c], static_cast<double>(k));
-    }
+  for (int c = 0; c < 3; ++c) {
+    a[c] = p.accel.gm_a[c]; bgm[c] = p.accel.gm_b[c]; wdc[c] = p.accel.wd[c];
+    a[3 + c] = p.gyro.gm_a[c]; bgm[3 + c] = p.gyro.gm_b[c]; wdc[3 + c] = p.gyro.wd[c];
   }
   double phase[3] = {0.0, 0.0, 0.0};
   if (p.gyro.vib_type == 2) {
@@ -68,92 +72,138 @@ __global__ void __launch_bounds__(kNoiseThreads, 2) imu_noise_kernel(const __gri
 #pragma unroll
     for (int c = 0; c < 6; ++c) carry[c] = p.seg_carry[(run * p.nseg + seg) * 6 + c];
   }
-  __syncthreads();
 
-  for (int64_t tile0 = seg_lo; tile0 < seg_hi; tile0 += kNoiseThreads) {
-    const int64_t t = tile0 + i;
-    const bool live = t < seg_hi;
-    double m[6], z[6];
-    if (live && p.pass == 1) {   // only the Gauss-Markov drives matter
+  for (int64_t tile0 = seg_lo; tile0 < seg_hi; tile0 += kNoiseTile) {
+    const int cnt = static_cast<int>(min64(kNoiseTile, seg_hi - tile0));
+    // ---- the thread's stretch: measurements without the drift at its start, zero-state response ----
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, A[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+#pragma unroll 1
+    for (int q = 0; q < kNoisePer; ++q) {
+      const int el = tid * kNoisePer + q;
+      if (el < cnt) {
+        const int64_t t = tile0 + el;
+        double m[6], z[6];
+        if (p.pass == 1) {   // only the Gauss-Markov drives matter
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        z[c] = normal_pair(static_cast<uint32_t>(t), kDrawAccel + c, run_lo, run_hi, p.k0, p.k1).z0;
-        z[3 + c] = normal_pair(static_cast<uint32_t>(t), kDrawGyro + c, run_lo, run_hi, p.k0, p.k1).z0;
-        m[c] = m[3 + c] = 0.0;
+          for (int c = 0; c < 6; ++c) {
+            z[c] = normal_pair(static_cast<uint32_t>(t), c, run_lo, run_hi, p.k0, p.k1).z0;
+            m[c] = 0.0;
+          }
+        } else {
+          noisy_sample(p, p.ref_accel + t * 3, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo, run_hi, run,
+                       phase, m, m + 3, z, z + 3);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          m[c] += r[c] + wdc[c] * z[c];          // + zero-state drift of the stretch (+ white drift)
+          r[c] = fma(a[c], r[c], bgm[c] * z[c]);
+          A[c] *= a[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          stage[0][el * 3 + c] = m[c];
+          stage[1][el * 3 + c] = m[3 + c];
+        }
       }
-    } else if (live) {
-      noisy_sample(p, p.ref_accel + t * 3, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo,
-                   run_hi, run, phase, m, m + 3, z, z + 3);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) m[c] = z[c] = 0.0;
     }
-    // The six Gauss-Markov recurrences d[t+1] = a d[t] + b z[t] as affine block scans, together:
-    // warp-level inclusive scans (shuffles with powers of a), the warp totals combined by 48
-    // threads, two barriers per tile.  y_i = sum_{q<=i} a^{i-q} b z_q (zero state at the tile
-    // start), d[tile0 + i] = a^i carry + y_{i-1}.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double y[6];
+    // ---- affine scan over the threads, six channels: (A, E) o (A', E') = (A A', A' E + E') -------
+    double sA[6], sE[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      const TriadNoise& e = (c < 3) ? p.accel : p.gyro;
-      y[c] = e.gm_b[c % 3] * z[c];
+      sA[c] = A[c];
+      sE[c] = r[c];
     }
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const double u = __shfl_up_sync(0xffffffffu, y[c], off);
-        if (lane >= off) y[c] += apow[c][off] * u;
+        const double uA = __shfl_up_sync(0xffffffffu, sA[c], off);
+        const double uE = __shfl_up_sync(0xffffffffu, sE[c], off);
+        if (lane >= off) {
+          sE[c] = fma(sA[c], uE, sE[c]);
+          sA[c] *= uA;
+        }
       }
     }
     if (lane == 31) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) sh_w[c][warp] = y[c];
+      for (int c = 0; c < 6; ++c) {
+        wtot[c][warp][0] = sA[c];
+        wtot[c][warp][1] = sE[c];
+      }
     }
-    __syncthreads();
-    if (threadIdx.x < 6 * (kNoiseWarps + 1)) {
-      // thread (c, w): value at the end of warp w-1 from a zero state at the tile start
-      const int c = threadIdx.x / (kNoiseWarps + 1), w = threadIdx.x % (kNoiseWarps + 1);
-      double pre = 0.0;
-      for (int q = 0; q < w; ++q) pre = apow[c][32] * pre + sh_w[c][q];
-      sh_pre[c][w] = pre;
-    }
-    __syncthreads();
+    __syncthreads();   // warp totals; the staged tile is complete
+    double S[6];       // drift at the first sample of this thread's stretch
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      const TriadNoise& e = (c < 3) ? p.accel : p.gyro;
-      const int a = c % 3;
-      const double pre = sh_pre[c][warp];
-      const double yi = y[c] + apow[c][lane + 1] * pre;      // inclusive, whole tile
-      const double up = __shfl_up_sync(0xffffffffu, yi, 1);
-      const double ym1 = (lane == 0) ? pre : up;             // y_{i-1}; 0 for the first sample
-      const double d = apow[c][i] * carry[c] + ym1;
-      m[c] += d + e.wd[a] * z[c];
-      carry[c] = apow[c][kNoiseThreads] * carry[c] + sh_pre[c][kNoiseWarps];
-    }
-    if (live && p.pass == 0) {
-      const int64_t o = run * p.osr + t * p.ost;
+      double pA = 1.0, pE = 0.0;
+      for (int w = 0; w < warp; ++w) {
+        pE = fma(wtot[c][w][0], pE, wtot[c][w][1]);
+        pA *= wtot[c][w][0];
+      }
+      const double lA = __shfl_up_sync(0xffffffffu, sA[c], 1), lE = __shfl_up_sync(0xffffffffu, sE[c], 1);
+      if (lane > 0) {
+        pE = fma(lA, pE, lE);
+        pA *= lA;
+      }
+      S[c] = fma(pA, carry[c], pE);
+      double tA = 1.0, tE = 0.0;       // the tile's total, by every thread alike: the next carry
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        p.out_accel[o + c * p.osc] = m[c];
-        p.out_gyro[o + c * p.osc] = m[3 + c];
+      for (int w = 0; w < kNoiseWarps; ++w) {
+        tE = fma(wtot[c][w][0], tE, wtot[c][w][1]);
+        tA *= wtot[c][w][0];
+      }
+      carry[c] = fma(tA, carry[c], tE);
+    }
+    if (p.pass == 0) {
+      // ---- + a^q S on the thread's own samples, then the tile leaves in the caller's layout -------
+      double ap[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+#pragma unroll 1
+      for (int q = 0; q < kNoisePer; ++q) {
+        const int el = tid * kNoisePer + q;
+        if (el < cnt) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            stage[0][el * 3 + c] += ap[c] * S[c];
+            stage[1][el * 3 + c] += ap[3 + c] * S[3 + c];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ap[c] *= a[c];
+      }
+      __syncthreads();
+      const int64_t base = run * p.osr + tile0 * p.ost;
+      if (p.osc == 1 && p.ost == 3) {            // [R][n][3]: the staged tile is the output, verbatim
+        for (int e = tid; e < cnt * 3; e += kNoiseThreads) {
+          p.out_accel[base + e] = stage[0][e];
+          p.out_gyro[base + e] = stage[1][e];
+        }
+      } else {                                   // channel-major / time-major: consecutive threads, consecutive t
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          for (int el = tid; el < cnt; el += kNoiseThreads) {
+            p.out_accel[base + el * p.ost + c * p.osc] = stage[0][el * 3 + c];
+            p.out_gyro[base + el * p.ost + c * p.osc] = stage[1][el * 3 + c];
+          }
       }
       if (p.z_dump) {
-        // (acc_gm[3], acc_w[3], gyr_gm[3], gyr_w[3]); the white normals are recovered from
-        // the same Philox draws
-        double* zd = p.z_dump + (run * p.n + t) * 12;
+        // (acc_gm[3], acc_w[3], gyr_gm[3], gyr_w[3]) of every sample, recovered from the same Philox draws
+        for (int el = tid; el < cnt; el += kNoiseThreads) {
+          const int64_t t = tile0 + el;
+          double* zd = p.z_dump + (run * p.n + t) * 12;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const Normal2 za = normal_pair(static_cast<uint32_t>(t), kDrawAccel + c, run_lo, run_hi, p.k0, p.k1);
-          const Normal2 zg = normal_pair(static_cast<uint32_t>(t), kDrawGyro + c, run_lo, run_hi, p.k0, p.k1);
-          zd[c] = za.z0;
-          zd[3 + c] = za.z1;
-          zd[6 + c] = zg.z0;
-          zd[9 + c] = zg.z1;
+          for (int c = 0; c < 3; ++c) {
+            const Normal2 za = normal_pair(static_cast<uint32_t>(t), kDrawAccel + c, run_lo, run_hi, p.k0, p.k1);
+            const Normal2 zg = normal_pair(static_cast<uint32_t>(t), kDrawGyro + c, run_lo, run_hi, p.k0, p.k1);
+            zd[c] = za.z0;
+            zd[3 + c] = za.z1;
+            zd[6 + c] = zg.z0;
+            zd[9 + c] = zg.z1;
+          }
         }
       }
     }
+    __syncthreads();   // the stage and the warp totals are rewritten by the next tile
   }
   if (p.pass == 1 && threadIdx.x == 0) {
     // the tiles of a segment are whole (seg_len is a multiple of the tile) except in the last

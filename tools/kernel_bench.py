@@ -91,7 +91,7 @@ def main():
 
     # ---- K1 materialised noise (48 B written per run-step) --------------------------------
     rg = torch.zeros((4000, 3), dtype=torch.float64, device='cuda')
-    for runs in ((1024, 8192) if only in ('', 'K1') else ()):
+    for runs in ((1024, 8192, 65536) if only in ('', 'K1') else ()):
         ms = timed(lambda: engine.imu_noise(100.0, runs, rg, rg, MID_G, MID_A, 1), reps=3)
         rate = runs * 4000 / (ms * 1e-3)
         emit(kernel='K1 imu_noise_kernel', runs=runs, n=4000, ms=ms, run_steps_per_s=rate,
@@ -118,10 +118,33 @@ def main():
              hbm_frac=nser * n * 8.8 / ms / 1e6 / hbm)
         del x
 
+    # ---- K14 Allan with the series generated in the tile (K1 fused into K4) -----------------
+    for runs, n in (((64, 2000000), (256, 14400000)) if only in ('', 'K14') else ()):
+        rz = torch.zeros((n, 3), dtype=torch.float64, device='cuda')
+        ms = timed(lambda: engine.allan_mc(400.0, runs, rz, rz, MID_G, MID_A, 1), reps=2, warm=1)
+        emit(kernel='K14 allan_gen (fused K1+K4)', runs=runs, n=n, ms=ms,
+             sample_channels_per_s=runs * 6 * n / (ms * 1e-3),
+             dfma_slots_per_sample_channel=dfma.value / (runs * 6 * n / (ms * 1e-3)))
+        del rz
+
+    # ---- K7 loosely-coupled filter -----------------------------------------------------------
+    if only in ('', 'K7'):
+        gg0 = g[0]
+        gp = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'gps_90deg_rf0.npz')))
+        nav0 = np.concatenate([gg0['ref_att'], gg0['ref_pos'], gg0['ref_vel']], axis=1)
+        d0 = [engine.to_device(a) for a in (gg0['ref_gyro'], gg0['ref_accel'], nav0, gp['ref_gps'])]
+        idx = torch.from_numpy(np.rint(gp['gps_time'] * 100.0).astype(np.int64)).cuda()
+        vis = torch.ones(len(idx), dtype=torch.float64, device='cuda')
+        gerr = {'stdp': np.array([5.0, 5.0, 7.0]), 'stdv': np.array([0.05, 0.05, 0.05])}
+        for runs in (1250, 10000, 100000):
+            ms = timed(lambda: engine.ins_loose(100.0, runs, 1, MID_G, MID_A, gerr, gg0['ini'], d0[0], d0[1], d0[2],
+                                                d0[3], idx, vis), reps=3)
+            emit(kernel='K7 ekf_kernel', runs=runs, n=1000, ms=ms, run_steps_per_s=runs * 1000 / (ms * 1e-3))
+
     # ---- K5 PSD series ----------------------------------------------------------------------
     tab = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'psd.npz')))
     vib = {'type': 'psd', 'freq': tab['freq_a'], 'x': tab['sxx_a'], 'y': tab['sxx_a'], 'z': tab['sxx_a']}
-    for runs, n in (((64, 1000), (64, 40000)) if only in ('', 'K5') else ()):
+    for runs, n in (((64, 1000), (64, 40000), (2048, 1000), (2048, 6000), (2048, 40000)) if only in ('', 'K5') else ()):
         ms = timed(lambda: engine.psd_series(200.0, n, runs, 0, vib, 1), reps=3)
         emit(kernel='K5 psd_series', runs=runs, n=n, ms=ms, series_per_s=runs * 3 / (ms * 1e-3))
 
