@@ -26,7 +26,7 @@ OBJ = os.path.join(CSRC, '_obj')
 LIB = os.environ.get('B2INS_LIB') or os.path.join(CSRC, 'libb2ins.so')
 UNITS = ['b2ins_api.cu', 'mc_plain_rf0.cu', 'mc_plain_rf1.cu', 'mc_spec_rf0.cu', 'mc_spec_rf1.cu']
 DEPS = UNITS + ['internal.h', 'mc_plain_launch.cuh', 'mc_spec_launch.cuh', 'common.cuh', 'fastmath64.cuh',
-                'mech.cuh', 'mc_kernel.cuh', 'mc_spec_kernel.cuh', 'noise_kernel.cuh', 'stats_kernel.cuh',
+                'mech.cuh', 'mc_kernel.cuh', 'mc_spec_kernel.cuh', 'mc_av_kernel.cuh', 'noise_kernel.cuh', 'stats_kernel.cuh',
                 'allan_kernel.cuh', 'psd_kernel.cuh', 'gps_kernel.cuh', 'ekf_kernel.cuh', 'pathgen_host.h',
                 os.path.join('..', '..', 'include', 'b2ins.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

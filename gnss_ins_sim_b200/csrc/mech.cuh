@@ -382,4 +382,60 @@ B2_DEV void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel, double dt
   }
 }
 
+// ---- ref_frame 1, the step split in two (mc_av_kernel.cuh) ------------------------------------------
+// In the virtual inertial frame the attitude recurrence does not depend on velocity or position
+// (free_integration.py:104: euler_update_zyx(att[i-1], gyro[i-1], dt)), so one warp can run it ahead and
+// hand the sin/cos of every step to a second warp that does velocity and position (:109-116).
+struct AttState {
+  double yaw, pitch, roll;
+  SinCos3 sc;
+  double icp;   // dt / cos(pitch)
+};
+
+// attitude.euler_update_zyx + euler2dcm's sin/cos for the new angles: the attitude half of nav_step<1>
+B2_DEV void att_step(AttState& s, const Vec3& w, double dt, bool resync) {
+  const double t = b2_fma(w.z, s.sc.cr, w.y * s.sc.sr);
+  const double dy = t * s.icp;
+  const double dp = b2_fma(w.y, s.sc.cr, -(w.z * s.sc.sr)) * dt;
+  const double dr = b2_fma(dy, s.sc.sp, w.x * dt);
+  s.yaw += dy;
+  s.pitch += dp;
+  s.roll += dr;
+  const bool cold = resync | !(fabs(s.pitch) <= kHalfPi) | !(fabs(dy) <= kRotMax) |
+                    !(fabs(dp) <= kRotMax) | !(fabs(dr) <= kRotMax);
+  rot_small(s.sc.sy, s.sc.cy, dy);
+  rot_small(s.sc.sp, s.sc.cp, dp);
+  rot_small(s.sc.sr, s.sc.cr, dr);
+  if (__builtin_expect(cold, 0)) {
+    NavState n;            // the exact path works on the full state type
+    n.yaw = s.yaw; n.pitch = s.pitch; n.roll = s.roll;
+    n.pos = Vec3{0.0, 0.0, 0.0};
+    resync_exact<1>(n);
+    s.yaw = n.yaw; s.pitch = n.pitch; s.roll = n.roll;
+    s.sc = n.sc;
+  }
+  s.icp = rcp_nr(s.sc.cp) * dt;
+}
+
+struct VelState {
+  Vec3 vel_b, vel, pos;
+  double gdt;   // g dt
+};
+
+// free_integration.py:109-116 with the sin/cos of step i-1 (old) and step i (now)
+B2_DEV void vel_step(VelState& s, const Vec3& gyro, const Vec3& accel, const SinCos3& old, const SinCos3& now,
+                     double dt) {
+  const double cpg = old.cp * s.gdt;
+  const Vec3 cgdt{-old.sp * s.gdt, cpg * old.sr, cpg * old.cr};
+  const Vec3 wxv = cross3(gyro, s.vel_b);
+  const Vec3 vel_old = s.vel;
+  s.vel_b.x = b2_fma(-wxv.x, dt, b2_fma(accel.x, dt, s.vel_b.x) + cgdt.x);
+  s.vel_b.y = b2_fma(-wxv.y, dt, b2_fma(accel.y, dt, s.vel_b.y) + cgdt.y);
+  s.vel_b.z = b2_fma(-wxv.z, dt, b2_fma(accel.z, dt, s.vel_b.z) + cgdt.z);
+  s.vel = rot_b2n(now, s.vel_b);
+  s.pos.x = b2_fma(vel_old.x, dt, s.pos.x);
+  s.pos.y = b2_fma(vel_old.y, dt, s.pos.y);
+  s.pos.z = b2_fma(vel_old.z, dt, s.pos.z);
+}
+
 }  // namespace b2ins

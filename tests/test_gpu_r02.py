@@ -29,7 +29,7 @@ def _mid():
 
 
 SHAPES = [(1, '3,1,0'), (1, '6,1,0'), (1, '0'), (2, '3,1,0'), (2, '6,1,0'), (4, '3,1,0'), (4, '3,1,1'),
-          (4, '6,1,0'), (8, '6,1,0'), (8, '1,2,0'), (16, '1,4,0'), (16, '1,4,1'), (32, '1,4,1'), (32, '0')]
+          (4, '6,1,0'), (4, '6,2,0'), (8, '6,1,0'), (8, '6,2,0'), (8, '1,2,0'), (16, '1,4,0'), (16, '1,4,1'), (32, '1,4,1'), (32, '0')]
 
 
 @pytest.mark.parametrize('rf', [1, 0])
@@ -78,9 +78,10 @@ def test_ragged_run_counts_and_lengths_in_the_specialised_form(gpu):
     nav = np.concatenate([g['ref_att'], g['ref_pos'], g['ref_vel']], axis=1)
     for n in (1, 2, 7, 9, 129, 131, 777):
         dev = [engine.to_device(a) for a in (g['ref_gyro'][:n], g['ref_accel'][:n], nav[:n], g['ini'][None])]
-        for R, lanes in ((1, 4), (9, 4), (33, 1), (5, 8), (3, 16), (37, 2)):
+        for R, lanes, spec in ((1, 4, ''), (9, 4, ''), (33, 1, ''), (5, 8, ''), (3, 16, ''), (37, 2, ''),
+                               (9, 4, '6,2,0'), (5, 8, '6,2,0'), (1, 4, '6,2,0')):
             out = {}
-            for shape in ('', '0'):
+            for shape in (spec, '0'):
                 if shape:
                     os.environ['B2INS_MC_SHAPE'] = shape
                 try:
@@ -90,8 +91,8 @@ def test_ragged_run_counts_and_lengths_in_the_specialised_form(gpu):
                     out[shape] = (out[shape].end_err.cpu().numpy(), out[shape].end_state.cpu().numpy())
                 finally:
                     os.environ.pop('B2INS_MC_SHAPE', None)
-            assert np.abs(out[''][0] - out['0'][0]).max() < 1e-11, (n, R, lanes)
-            assert np.abs(out[''][1] - out['0'][1]).max() < 1e-9 * 5e6, (n, R, lanes)
+            assert np.abs(out[spec][0] - out['0'][0]).max() < 1e-11, (n, R, lanes, spec)
+            assert np.abs(out[spec][1] - out['0'][1]).max() < 1e-9 * 5e6, (n, R, lanes, spec)
 
 
 @pytest.mark.parametrize('rf', [1, 0])

@@ -17,7 +17,7 @@ MID_G = {'b': np.zeros(3), 'b_drift': np.full(3, 3.5 * np.pi / 180 / 3600),
          'b_corr': np.full(3, 100.0), 'arw': np.full(3, 0.25 * np.pi / 180 / 60)}
 MID_A = {'b': np.zeros(3), 'b_drift': np.full(3, 5e-5), 'b_corr': np.full(3, 100.0),
          'vrw': np.full(3, 0.03 / 60)}
-SHAPES = {1: ['3,1,0', '6,1,0', '0'], 2: ['3,1,0', '6,1,0'], 4: ['3,1,0', '6,1,0', '3,1,1'], 8: ['6,1,0'],
+SHAPES = {1: ['3,1,0', '6,1,0', '0'], 2: ['3,1,0', '6,1,0'], 4: ['3,1,0', '6,1,0', '6,2,0'], 8: ['6,1,0', '6,2,0'],
           16: ['1,4,0', '1,4,1'], 32: ['1,4,1']}
 
 
@@ -26,7 +26,7 @@ def main():
     sweeps = [(1000, [4, 8, 16, 32, 2]), (500, [4, 8, 16]), (2000, [2, 4, 1]), (4000, [1, 2, 4]),
               (8000, [1, 2]), (12500, [1, 2, 4]), (40000, [1, 2]), (100000, [1]), (1000000, [1])]
     if quick:
-        sweeps = [(1000, [4, 8, 16]), (12500, [1, 2])]
+        sweeps = [(1000, [4, 8]), (500, [8, 4]), (2000, [4, 2])]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     for rf in (1, 0):
         g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'traj_90deg_turn_100hz_rf%d.npz' % rf)))
