@@ -342,7 +342,7 @@ def run_b200(args):
         if world == 1:
             return engine.error_stats(res.end_err)
         if p2p is not None:
-            return p2p(res.end_err, R).cpu().numpy()
+            return p2p(res.end_err, R)          # stays on the device, like the N = 1 step: no host sync per step
         return merger(engine.error_stats(res.end_err), R)
 
     def barrier():
@@ -374,7 +374,7 @@ def run_b200(args):
     clocks = sampler.stop()
     dev_ms = allmax(sum(a.elapsed_time(b) for a, b in evs))
     value = total_runs * n * args.steps / (dev_ms * 1e-3)
-    stats = stats.cpu().numpy() if hasattr(stats, 'cpu') else stats
+    stats = stats.cpu().numpy().copy() if hasattr(stats, 'cpu') else stats
     k3x_timed_out = bool(p2p.timed_out()) if p2p is not None else False
 
     # ---- N > 1: the sharded statistics against ONE GPU doing all the runs -------------------

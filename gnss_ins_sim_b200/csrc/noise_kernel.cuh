@@ -44,9 +44,32 @@ struct NoiseParams {
   double* seg_end;
 };
 
-__global__ void __launch_bounds__(kNoiseThreads, 3) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
+// one triad (three channels of one sensor) of one sample: the measurement without the drift at the start of
+// the thread's stretch, and the stretch's zero-state drift response advanced by one sample
+template <int SENSOR>   // 0 accel (draws 0..2), 1 gyro (draws 3..5)
+__device__ __forceinline__ void triad_sample(const NoiseParams& p, const TriadNoise& e, const double* ref3, uint32_t t,
+                                             uint32_t run_lo, uint32_t run_hi, int64_t run, const double* phase,
+                                             bool drives_only, double* r3, double* out3) {
+  Normal2 z[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) z[c] = normal_pair(t, 3 * SENSOR + c, run_lo, run_hi, p.k0, p.k1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double m = 0.0;
+    if (!drives_only) {
+      m = (ref3[c] + e.b[c]) + e.w[c] * z[c].z1;
+      if (p.accel.vib_type | p.gyro.vib_type)   // uniform branch, off in the BASELINE configs
+        m += vib_term(e, c, SENSOR, t, run_lo, run_hi, p.k0, p.k1, run, phase);
+    }
+    out3[c] = m + r3[c] + e.wd[c] * z[c].z0;        // + zero-state drift of the stretch (+ white drift)
+    r3[c] = fma(e.gm_a[c], r3[c], e.gm_b[c] * z[c].z0);
+  }
+}
+
+__global__ void __launch_bounds__(kNoiseThreads, 4) imu_noise_kernel(const __grid_constant__ NoiseParams p) {
   __shared__ double stage[2][kNoiseTile * 3];     // accel, gyro of the tile, [sample][axis]
   __shared__ double wtot[6][kNoiseWarps][2];      // (A, E) of every warp's stretch, per channel
+  __shared__ double apow[kNoisePer + 1][6];       // a^q per channel
   const int segs = (p.pass == 1) ? p.nseg - 1 : p.nseg;
   const int64_t run = blockIdx.x / segs;
   const int seg = static_cast<int>(blockIdx.x % segs);
@@ -55,11 +78,13 @@ __global__ void __launch_bounds__(kNoiseThreads, 3) imu_noise_kernel(const __gri
   const int64_t grun = p.run_offset + run;
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double a[6], bgm[6], wdc[6];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    a[c] = p.accel.gm_a[c]; bgm[c] = p.accel.gm_b[c]; wdc[c] = p.accel.wd[c];
-    a[3 + c] = p.gyro.gm_a[c]; bgm[3 + c] = p.gyro.gm_b[c]; wdc[3 + c] = p.gyro.wd[c];
+  if (tid < 6) {
+    const double a = (tid < 3) ? p.accel.gm_a[tid] : p.gyro.gm_a[tid - 3];
+    double v = 1.0;
+    for (int q = 0; q <= kNoisePer; ++q) {
+      apow[q][tid] = v;
+      v *= a;
+    }
   }
   double phase[3] = {0.0, 0.0, 0.0};
   if (p.gyro.vib_type == 2) {
@@ -72,45 +97,33 @@ __global__ void __launch_bounds__(kNoiseThreads, 3) imu_noise_kernel(const __gri
 #pragma unroll
     for (int c = 0; c < 6; ++c) carry[c] = p.seg_carry[(run * p.nseg + seg) * 6 + c];
   }
+  __syncthreads();
 
   for (int64_t tile0 = seg_lo; tile0 < seg_hi; tile0 += kNoiseTile) {
     const int cnt = static_cast<int>(min64(kNoiseTile, seg_hi - tile0));
-    // ---- the thread's stretch: measurements without the drift at its start, zero-state response ----
-    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, A[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+    // ---- the thread's stretch: one sensor triad at a time (three Box-Muller chains in flight) -------
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int mine = cnt - tid * kNoisePer;                 // live samples of this thread's stretch
+    mine = mine < 0 ? 0 : (mine > kNoisePer ? kNoisePer : mine);
 #pragma unroll 1
-    for (int q = 0; q < kNoisePer; ++q) {
+    for (int q = 0; q < mine; ++q) {
       const int el = tid * kNoisePer + q;
-      if (el < cnt) {
-        const int64_t t = tile0 + el;
-        double m[6], z[6];
-        if (p.pass == 1) {   // only the Gauss-Markov drives matter
+      const int64_t t = tile0 + el;
+      double m3[3];
+      triad_sample<0>(p, p.accel, p.ref_accel + t * 3, static_cast<uint32_t>(t), run_lo, run_hi, run, phase,
+                      p.pass == 1, r, m3);
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            z[c] = normal_pair(static_cast<uint32_t>(t), c, run_lo, run_hi, p.k0, p.k1).z0;
-            m[c] = 0.0;
-          }
-        } else {
-          noisy_sample(p, p.ref_accel + t * 3, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo, run_hi, run,
-                       phase, m, m + 3, z, z + 3);
-        }
+      for (int c = 0; c < 3; ++c) stage[0][el * 3 + c] = m3[c];
+      triad_sample<1>(p, p.gyro, p.ref_gyro + t * 3, static_cast<uint32_t>(t), run_lo, run_hi, run, phase,
+                      p.pass == 1, r + 3, m3);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          m[c] += r[c] + wdc[c] * z[c];          // + zero-state drift of the stretch (+ white drift)
-          r[c] = fma(a[c], r[c], bgm[c] * z[c]);
-          A[c] *= a[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          stage[0][el * 3 + c] = m[c];
-          stage[1][el * 3 + c] = m[3 + c];
-        }
-      }
+      for (int c = 0; c < 3; ++c) stage[1][el * 3 + c] = m3[c];
     }
     // ---- affine scan over the threads, six channels: (A, E) o (A', E') = (A A', A' E + E') -------
     double sA[6], sE[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      sA[c] = A[c];
+      sA[c] = apow[mine][c];
       sE[c] = r[c];
     }
 #pragma unroll
@@ -157,19 +170,14 @@ __global__ void __launch_bounds__(kNoiseThreads, 3) imu_noise_kernel(const __gri
     }
     if (p.pass == 0) {
       // ---- + a^q S on the thread's own samples, then the tile leaves in the caller's layout -------
-      double ap[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
 #pragma unroll 1
-      for (int q = 0; q < kNoisePer; ++q) {
+      for (int q = 0; q < mine; ++q) {
         const int el = tid * kNoisePer + q;
-        if (el < cnt) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            stage[0][el * 3 + c] += ap[c] * S[c];
-            stage[1][el * 3 + c] += ap[3 + c] * S[3 + c];
-          }
+        for (int c = 0; c < 3; ++c) {
+          stage[0][el * 3 + c] += apow[q][c] * S[c];
+          stage[1][el * 3 + c] += apow[q][3 + c] * S[3 + c];
         }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) ap[c] *= a[c];
       }
       __syncthreads();
       const int64_t base = run * p.osr + tile0 * p.ost;
