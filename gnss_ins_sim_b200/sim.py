@@ -25,6 +25,7 @@ Multi-GPU: runs are sharded by rank when torch.distributed is initialised (dist.
 """
 import math
 import os
+import weakref
 from collections.abc import Mapping
 
 import numpy as np
@@ -216,10 +217,10 @@ class _LazyDevice(dict):
 
     def __init__(self, sim):
         super().__init__()
-        self._sim = sim
+        self._sim = weakref.ref(sim)     # no reference cycle: a Sim is freed (with its device arrays) when dropped
 
     def __missing__(self, key):
-        sim = self._sim
+        sim = self._sim()
         src = sim._nav if key == 'ref_nav' else sim._traj[key]
         self[key] = engine.to_device(src)
         return self[key]
@@ -233,7 +234,16 @@ class LazyRuns(Mapping):
     experiment with 10^5 runs must not spend its time making 10^5 Python strings)."""
 
     def __init__(self, sim, name, count, prefix=None):
-        self._sim, self._name, self._count, self._prefix = sim, name, int(count), prefix
+        # a weak reference: Sim.data -> LazyRuns -> Sim would be a cycle that only the cyclic collector frees,
+        # and a Sim owns device and pinned buffers
+        self._sim_ref, self._name, self._count, self._prefix = weakref.ref(sim), name, int(count), prefix
+
+    @property
+    def _sim(self):
+        sim = self._sim_ref()
+        if sim is None:
+            raise ReferenceError('the Sim these run histories belong to no longer exists')
+        return sim
 
     def _key(self, r):
         return r if self._prefix is None else '%s_%d' % (self._prefix, r)
