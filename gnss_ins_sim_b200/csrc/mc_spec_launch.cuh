@@ -39,6 +39,7 @@ bool B2_SPEC_NAME(const McParams& p, const McShape& sh, cudaStream_t s) {
     case 4310: launch_one<4, 3, 1, false, 2>(p, s); return true;
     case 4311: launch_one<4, 3, 1, true, 2>(p, s); return true;
     case 4610: launch_one<4, 6, 1, false, 1>(p, s); return true;
+    case 4611: launch_one<4, 6, 1, true, 1>(p, s); return true;
 #if B2_RF == 1
     case 4620: launch_av<4>(p, s); return true;
     case 8620: launch_av<8>(p, s); return true;

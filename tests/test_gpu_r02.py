@@ -29,7 +29,7 @@ def _mid():
 
 
 SHAPES = [(1, '3,1,0'), (1, '6,1,0'), (1, '0'), (2, '3,1,0'), (2, '6,1,0'), (4, '3,1,0'), (4, '3,1,1'),
-          (4, '6,1,0'), (4, '6,2,0'), (8, '6,1,0'), (8, '6,2,0'), (8, '1,2,0'), (16, '1,4,0'), (16, '1,4,1'), (32, '1,4,1'), (32, '0')]
+          (4, '6,1,0'), (4, '6,1,1'), (4, '6,2,0'), (8, '6,1,0'), (8, '6,2,0'), (8, '1,2,0'), (16, '1,4,0'), (16, '1,4,1'), (32, '1,4,1'), (32, '0')]
 
 
 @pytest.mark.parametrize('rf', [1, 0])

@@ -17,7 +17,7 @@ MID_G = {'b': np.zeros(3), 'b_drift': np.full(3, 3.5 * np.pi / 180 / 3600),
          'b_corr': np.full(3, 100.0), 'arw': np.full(3, 0.25 * np.pi / 180 / 60)}
 MID_A = {'b': np.zeros(3), 'b_drift': np.full(3, 5e-5), 'b_corr': np.full(3, 100.0),
          'vrw': np.full(3, 0.03 / 60)}
-SHAPES = {1: ['3,1,0', '6,1,0', '0'], 2: ['3,1,0', '6,1,0'], 4: ['3,1,0', '6,1,0', '6,2,0'], 8: ['6,1,0', '6,2,0'],
+SHAPES = {1: ['3,1,0', '6,1,0', '0'], 2: ['3,1,0', '6,1,0'], 4: ['3,1,0', '6,1,0', '6,1,1', '6,2,0'], 8: ['6,1,0', '6,2,0'],
           16: ['1,4,0', '1,4,1'], 32: ['1,4,1']}
 
 
