@@ -830,16 +830,8 @@ int b2ins_ins_loose_f64(const b2ins_ekf_config* cfg, const double* ref_gyro, con
   p.dump_runs = ndump ? cfg->dump_runs : 0;
   p.dump_stride = cfg->dump_stride > 1 ? cfg->dump_stride : 1;
   p.dump_rows = (cfg->n + p.dump_stride - 1) / p.dump_stride;
-  const size_t smem = sizeof(double) * kEkfN * kEkfN * kEkfThreads;
-  static int attr_dev = -1;
-  int dev = 0;
-  CU_CHECK(cudaGetDevice(&dev));
-  if (attr_dev != dev) {
-    CU_CHECK(cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_dev = dev;
-  }
-  const unsigned grid = static_cast<unsigned>((cfg->runs + kEkfThreads - 1) / kEkfThreads);
-  ekf_kernel<<<grid, kEkfThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const unsigned grid = static_cast<unsigned>((cfg->runs + kEkfRuns - 1) / kEkfRuns);
+  ekf_kernel<<<grid, kEkfThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CU_CHECK(cudaGetLastError());
   return B2INS_OK;
 }

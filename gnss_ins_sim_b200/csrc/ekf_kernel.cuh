@@ -8,13 +8,15 @@
 // the sensor models that feed it (pathgen.acc_gen / gyro_gen :441-594, gps_gen :596-625, the same
 // Philox streams as K12 / K6) and the strapdown step (free_integration.py:133-172 = nav_step<0>).
 //
-// One thread owns one Monte-Carlo run for the whole series (the filter is serial in time and its
-// GPS epochs are common to all runs, so a warp never diverges): the nominal state, the bias
-// estimates and the generator's Gauss-Markov states live in registers, the 15 x 15 covariance in
-// shared memory as P[element][thread] (bank-conflict-free; 57.6 KB per 32-thread CTA, three CTAs per
-// SM).  Per IMU sample: six Box-Muller pairs, one strapdown step, and P <- Phi P Phi^T + Q done as two
-// in-place sweeps that use the block structure of Phi (about 1100 FMA instead of 6750).  Per GPS
-// sample (every fs / fs_gps steps): three more pairs, six scalar updates, the correction.
+// Four lanes own one Monte-Carlo run for the whole series (the filter is serial in time and its GPS
+// epochs are common to all runs, so a warp never diverges on them): the nominal state and the bias
+// estimates are replicated over the four lanes, everything else is shared out -- the six Box-Muller
+// pairs of a sample, the columns / rows of the covariance sweeps, the rows of the rank-one updates.  The
+// 15 x 15 covariance lives in shared memory as P[element][run of the CTA] (14.4 KB per 32-thread CTA of
+// eight runs; every warp access is bank-conflict-free).  Per IMU sample: six Box-Muller pairs, one
+// strapdown step, and P <- Phi P Phi^T + Q done as two in-place sweeps that use the block structure of
+// Phi (about 1100 FMA instead of 6750).  Per GPS sample (every fs / fs_gps steps): three more pairs, six
+// scalar updates, the correction.
 #pragma once
 #include "mc_kernel.cuh"
 #include "gps_kernel.cuh"
@@ -98,32 +100,56 @@ __device__ __forceinline__ void set_attitude(NavState& st, double yaw, double pi
   st.icp = rcp_nr(st.sc.cp) * dt;
 }
 
+// FOUR lanes per run (a quad): the nominal state is replicated, everything else is shared out --
+// the six Box-Muller pairs of a sample (lane q makes channel q, lanes 0 and 1 also channels 4 and 5; the
+// Gauss-Markov state of a channel lives in its owner), the columns / rows of the two covariance sweeps,
+// the rows of the rank-one updates.  P[element][run of the CTA] in shared memory.
+constexpr int kEkfQ = 4;
+constexpr int kEkfRuns = kEkfThreads / kEkfQ;     // 8 runs per CTA
+
+// Row (= column) of P that lane q works on in its m-th turn (m = 0..3, a compile-time constant after
+// unrolling): lanes 0..2 take row q of the position, velocity, attitude and accelerometer-bias blocks,
+// lane 3 takes the three gyro-bias rows and sits out the fourth turn (it repeats its first row and
+// stores nothing).  A turn therefore has ONE block type on lanes 0..2, which makes the process-noise
+// terms of the second sweep compile-time, and any two lanes of a half-warp differ by an odd number of
+// rows / columns, which keeps every 64-bit access of a warp on distinct banks.
+__device__ __forceinline__ int ekf_own(int q, int m) {
+  const int blk = (m == 3) ? 4 : m;
+  return (q < 3) ? 3 * blk + q : ((m < 3) ? 9 + m : 9);
+}
+
 __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant__ EkfParams p) {
-  extern __shared__ double Psm[];           // [225][kEkfThreads]
-  const int tid = threadIdx.x;
-  const int64_t run_raw = static_cast<int64_t>(blockIdx.x) * kEkfThreads + tid;
+  __shared__ double Psm[kEkfN * kEkfN * kEkfRuns];      // 14.4 KB
+  const int lane = threadIdx.x;
+  // lane = q * 8 + rs: the eight runs of a quad index are neighbours, so a warp's 64-bit accesses to
+  // P[element][run] fall on distinct banks whether the four q's differ in the column (sweep 1) or in
+  // the row (sweep 2: rows are 15 * 8 doubles apart, half a bank cycle)
+  const int q = lane >> 3, rs = lane & 7;
+  const int64_t run_raw = static_cast<int64_t>(blockIdx.x) * kEkfRuns + rs;
   const bool active = run_raw < p.runs;
   const int64_t run = active ? run_raw : p.runs - 1;
   const int64_t grun = p.run_offset + run;
   const uint32_t run_lo = static_cast<uint32_t>(grun), run_hi = static_cast<uint32_t>(grun >> 32);
-  const bool dump = active && run < p.dump_runs && p.out_att;
+  const bool dump = active && q == 0 && run < p.dump_runs && p.out_att;
   const double dt = p.dt;
-  auto P = [&](int i, int j) -> double& { return Psm[(i * kEkfN + j) * kEkfThreads + tid]; };
+  auto P = [&](int i, int j) -> double& { return Psm[(i * kEkfN + j) * kEkfRuns + rs]; };
+  auto quad = [&](double v, int owner) { return __shfl_sync(0xffffffffu, v, owner * kEkfRuns + rs); };
 
   // GPS noise of the generator: horizontal sigmas in radians with the radii at the FIRST reference
   // sample, as pathgen.gps_gen does (pathgen.py:617-620)
   double sdp0 = p.stdp[0], sdp1 = p.stdp[1];
-  {
+  if (p.m > 0) {
     const GeoParam gp = geo_param(p.ref_gps[0], p.ref_gps[2]);
     sdp0 = div_nr(sdp0, gp.rm);
     sdp1 = div_nr(div_nr(sdp1, gp.rn), gp.cl);
   }
 
   // ---- initial covariance and nominal state: truth + a draw from P0 -----------------------------
-#pragma unroll 1
-  for (int e = 0; e < kEkfN * kEkfN; ++e) Psm[e * kEkfThreads + tid] = 0.0;
-#pragma unroll
-  for (int i = 0; i < kEkfN; ++i) P(i, i) = p.p0[i];
+  for (int m = 0; m < 4; ++m) {
+    const int r = ekf_own(q, m);
+    if (q < 3 || m < 3)
+      for (int c = 0; c < kEkfN; ++c) P(r, c) = (r == c) ? p.p0[r] : 0.0;
+  }
   double e0[10];
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -152,9 +178,19 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
     dcm2euler(c, &y, &pt, &r);
     set_attitude(st, y, pt, r, dt);
   }
-  double bg[3] = {0.0, 0.0, 0.0}, ba[3] = {0.0, 0.0, 0.0};       // bias estimates
-  double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};              // generator: GM drift d[i] (accel, gyro)
-  double phase[3] = {0.0, 0.0, 0.0};
+  double bg[3] = {0.0, 0.0, 0.0}, ba[3] = {0.0, 0.0, 0.0};       // bias estimates (replicated)
+  // the generator's channels of this lane: c0 = q (accel x y z, gyro x), c1 = q + 4 (gyro y z) for q < 2
+  const int c0 = q, c1 = q + 4;
+  const bool two = q < 2;
+  auto model = [&](int c, double* b, double* w, double* wd, double* ga, double* gb) {
+    const TriadNoise& e = (c < 3) ? p.accel : p.gyro;
+    const int ax = c % 3;
+    *b = e.b[ax]; *w = e.w[ax]; *wd = e.wd[ax]; *ga = e.gm_a[ax]; *gb = e.gm_b[ax];
+  };
+  double b0, w0, wd0, ga0, gb0, b1, w1, wd1, ga1, gb1;
+  model(c0, &b0, &w0, &wd0, &ga0, &gb0);
+  model(two ? c1 : c0, &b1, &w1, &wd1, &ga1, &gb1);
+  double carry0 = 0.0, carry1 = 0.0;                              // d[i] of the lane's channels
   double nees[3] = {0.0, 0.0, 0.0};
   int inside[kEkfN];
 #pragma unroll
@@ -162,17 +198,20 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
   int epochs = 0;
   int64_t jg = 0;                          // next GPS row
   int64_t next_gps = p.m > 0 ? p.gps_idx[0] : -1;
+  __syncwarp();
 
   for (int64_t i = 0; i < p.n; ++i) {
     // ================= GPS sample of IMU sample i: update, then the consistency record ==========
     if (i == next_gps) {
       if (p.gps_vis[jg] > 0.0) {
+        // the three GPS pairs: lane q < 3 makes pair q, the quad shares them
+        Normal2 zz{0.0, 0.0};
+        if (q < 3) zz = normal_pair(static_cast<uint32_t>(jg), kPairGps + q, run_lo, run_hi, p.k0, p.k1);
         double zn[6];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const Normal2 zz = normal_pair(static_cast<uint32_t>(jg), kPairGps + j, run_lo, run_hi, p.k0, p.k1);
-          zn[2 * j] = zz.z0;
-          zn[2 * j + 1] = zz.z1;
+          zn[2 * j] = quad(zz.z0, j);
+          zn[2 * j + 1] = quad(zz.z1, j);
         }
         const double* rg = p.ref_gps + jg * 6;
         const GeoParam gp = geo_param_sc(st.sl, st.cl, st.pos.z);
@@ -186,44 +225,37 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
         zm[5] = st.vel.z - (rg[5] + p.stdv[2] * zn[5]);
         double x[kEkfN];
 #pragma unroll
-        for (int q = 0; q < kEkfN; ++q) x[q] = 0.0;
-#pragma unroll 1
+        for (int c = 0; c < kEkfN; ++c) x[c] = 0.0;
+#pragma unroll
         for (int k = 0; k < 6; ++k) {
+          // row k of P (= column k: P is symmetric), read by every lane before its owner rewrites it
+          double row[kEkfN];
+#pragma unroll
+          for (int c = 0; c < kEkfN; ++c) row[c] = P(k, c);
+          __syncwarp();
           const double rk = (k < 3) ? p.stdp[k] * p.stdp[k] : p.stdv[k - 3] * p.stdv[k - 3];
-          const double inv_s = 1.0 / (P(k, k) + rk);
-          double K[kEkfN], row[kEkfN];
+          const double inv_s = 1.0 / (row[k] + rk);
+          const double innov = zm[k] - x[k];
 #pragma unroll
-          for (int q = 0; q < kEkfN; ++q) {
-            K[q] = P(q, k) * inv_s;
-            row[q] = P(k, q);
-          }
-          double xk = 0.0, zk = 0.0;   // x[k], zm[k] with a run-time index: selects, not local-memory arrays
+          for (int c = 0; c < kEkfN; ++c) x[c] = fma(row[c] * inv_s, innov, x[c]);      // x += K innov, K = P[:,k] / s
+          // P <- P - P[:,k] P[k,:] / s on this lane's rows.  The product P[a,k] P[b,k] is formed first, so
+          // the (a,b) and (b,a) entries -- computed by different lanes -- get the same bits: the symmetric
+          // result the spec reaches by (P + P^T) / 2
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            xk = (q == k) ? x[q] : xk;
-            zk = (q == k) ? zm[q] : zk;
-          }
-          const double innov = zk - xk;
+          for (int m = 0; m < 4; ++m) {
+            const int a = ekf_own(q, m);
+            const double pak = P(a, k);
+            double v[kEkfN];
 #pragma unroll
-          for (int q = 0; q < kEkfN; ++q) x[q] += K[q] * innov;
-          // P <- P - K P[k,:], then (P + P^T)/2 as the spec does
-#pragma unroll 1
-          for (int a = 0; a < kEkfN; ++a) {
-            double Ka = 0.0;
+            for (int b = 0; b < kEkfN; ++b) v[b] = fma(-(pak * row[b]), inv_s, P(a, b));
+            if (q < 3 || m < 3) {
 #pragma unroll
-            for (int q = 0; q < kEkfN; ++q) Ka = (q == a) ? K[q] : Ka;
-#pragma unroll
-            for (int b = 0; b < kEkfN; ++b) P(a, b) -= Ka * row[b];
-          }
-#pragma unroll 1
-          for (int a = 0; a < kEkfN; ++a)
-            for (int b = a + 1; b < kEkfN; ++b) {
-              const double s = 0.5 * (P(a, b) + P(b, a));
-              P(a, b) = s;
-              P(b, a) = s;
+              for (int b = 0; b < kEkfN; ++b) P(a, b) = v[b];
             }
+          }
+          __syncwarp();
         }
-        // ---- close the loop -----------------------------------------------------------------
+        // ---- close the loop (replicated) ------------------------------------------------------
         st.pos.x -= x[0] / rmh;
         st.pos.y -= x[1] / rnh;
         st.pos.z += x[2];
@@ -242,6 +274,10 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
         }
       }
       if (i >= p.stats_start) {
+        // the generator's drift d[i] of every channel, from its owner
+        double dch[6];
+        dch[0] = quad(carry0, 0); dch[1] = quad(carry0, 1); dch[2] = quad(carry0, 2); dch[3] = quad(carry0, 3);
+        dch[4] = quad(carry1, 0); dch[5] = quad(carry1, 1);
         const double* rn9 = p.ref_nav + i * 9;
         const GeoParam gp = geo_param(rn9[3], rn9[5]);
         double e[kEkfN];
@@ -265,8 +301,8 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
         e[8] = -0.5 * (m10 - m01);
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
-          e[9 + c3] = bg[c3] - (p.gyro.b[c3] + carry[3 + c3]);
-          e[12 + c3] = ba[c3] - (p.accel.b[c3] + carry[c3]);
+          e[9 + c3] = bg[c3] - (p.gyro.b[c3] + dch[3 + c3]);
+          e[12 + c3] = ba[c3] - (p.accel.b[c3] + dch[c3]);
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -278,7 +314,7 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
           nees[b] += nees3(a9, e + 3 * b);
         }
 #pragma unroll
-        for (int q = 0; q < kEkfN; ++q) inside[q] += (fabs(e[q]) <= 3.0 * sqrt(P(q, q))) ? 1 : 0;
+        for (int c = 0; c < kEkfN; ++c) inside[c] += (e[c] * e[c] <= 9.0 * P(c, c)) ? 1 : 0;      // |e| <= 3 sigma
         ++epochs;
       }
       ++jg;
@@ -298,19 +334,24 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
       }
     }
     if (i == p.n - 1) break;
-    // ================= the measurements of sample i (the K12 generator) ==========================
-    double ma[3], mg[3], za[3], zg[3];
-    noisy_sample(p, p.ref_accel + i * 3, p.ref_gyro + i * 3, static_cast<uint32_t>(i), run_lo, run_hi, run, phase,
-                 ma, mg, za, zg);
-#pragma unroll
-    for (int c3 = 0; c3 < 3; ++c3) {
-      ma[c3] += carry[c3] + p.accel.wd[c3] * za[c3];
-      mg[c3] += carry[3 + c3] + p.gyro.wd[c3] * zg[c3];
-      carry[c3] = fma(p.accel.gm_a[c3], carry[c3], p.accel.gm_b[c3] * za[c3]);
-      carry[3 + c3] = fma(p.gyro.gm_a[c3], carry[3 + c3], p.gyro.gm_b[c3] * zg[c3]);
+    // ================= the measurements of sample i (the K12 generator, shared out over the quad) ==
+    double m0, m1 = 0.0;
+    {
+      const uint32_t t = static_cast<uint32_t>(i);
+      const double* ref0 = (c0 < 3) ? p.ref_accel + i * 3 + c0 : p.ref_gyro + i * 3 + (c0 - 3);
+      const Normal2 z0 = normal_pair(t, static_cast<uint32_t>(c0), run_lo, run_hi, p.k0, p.k1);
+      m0 = ((ref0[0] + b0) + w0 * z0.z1) + (carry0 + wd0 * z0.z0);
+      carry0 = fma(ga0, carry0, gb0 * z0.z0);
+      // every lane runs a second chain (lanes 2 and 3 repeat their first draw and drop the result): no
+      // divergent branch, and the two Box-Muller chains of a lane interleave
+      const int cc = two ? c1 : c0;
+      const double* ref1 = (cc < 3) ? p.ref_accel + i * 3 + cc : p.ref_gyro + i * 3 + (cc - 3);
+      const Normal2 z1 = normal_pair(t, static_cast<uint32_t>(cc), run_lo, run_hi, p.k0, p.k1);
+      m1 = ((ref1[0] + b1) + w1 * z1.z1) + (carry1 + wd1 * z1.z0);
+      carry1 = two ? fma(ga1, carry1, gb1 * z1.z0) : 0.0;
     }
-    const Vec3 w{mg[0] - bg[0], mg[1] - bg[1], mg[2] - bg[2]};
-    const Vec3 f{ma[0] - ba[0], ma[1] - ba[1], ma[2] - ba[2]};
+    const Vec3 f{quad(m0, 0) - ba[0], quad(m0, 1) - ba[1], quad(m0, 2) - ba[2]};
+    const Vec3 w{quad(m0, 3) - bg[0], quad(m1, 0) - bg[1], quad(m1, 1) - bg[2]};
     // ================= covariance: P <- Phi P Phi^T + Q with the blocks of Phi ====================
     {
       const Dcm c = dcm_from_sincos(st.sc);          // n -> b of sample i; b -> n is its transpose
@@ -318,70 +359,90 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
                             c.c02 * dt, c.c12 * dt, c.c22 * dt};      // C(b->n) dt, row-major
       const Vec3 fn = rot_b2n(st.sc, f);
       const double sx = fn.x * dt, sy = fn.y * dt, sz = fn.z * dt;    // [f_n x] dt = [[0,-sz,sy],[sz,0,-sx],[-sy,sx,0]]
-      // sweep 1, column by column: A = Phi P
-#pragma unroll 1
-      for (int j = 0; j < kEkfN; ++j) {
+      // sweep 1, this lane's columns: A = Phi P
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = ekf_own(q, m);
         double col[kEkfN];
 #pragma unroll
-        for (int q = 0; q < kEkfN; ++q) col[q] = P(q, j);
-        P(0, j) = fma(dt, col[3], col[0]);
-        P(1, j) = fma(dt, col[4], col[1]);
-        P(2, j) = fma(dt, col[5], col[2]);
-        P(3, j) = col[3] + (-sz * col[7] + sy * col[8]) - (cb[0] * col[12] + cb[1] * col[13] + cb[2] * col[14]);
-        P(4, j) = col[4] + (sz * col[6] - sx * col[8]) - (cb[3] * col[12] + cb[4] * col[13] + cb[5] * col[14]);
-        P(5, j) = col[5] + (-sy * col[6] + sx * col[7]) - (cb[6] * col[12] + cb[7] * col[13] + cb[8] * col[14]);
-        P(6, j) = col[6] + (cb[0] * col[9] + cb[1] * col[10] + cb[2] * col[11]);
-        P(7, j) = col[7] + (cb[3] * col[9] + cb[4] * col[10] + cb[5] * col[11]);
-        P(8, j) = col[8] + (cb[6] * col[9] + cb[7] * col[10] + cb[8] * col[11]);
+        for (int r = 0; r < kEkfN; ++r) col[r] = P(r, j);
+        double o[kEkfN];
+        o[0] = fma(dt, col[3], col[0]);
+        o[1] = fma(dt, col[4], col[1]);
+        o[2] = fma(dt, col[5], col[2]);
+        o[3] = col[3] + (-sz * col[7] + sy * col[8]) - (cb[0] * col[12] + cb[1] * col[13] + cb[2] * col[14]);
+        o[4] = col[4] + (sz * col[6] - sx * col[8]) - (cb[3] * col[12] + cb[4] * col[13] + cb[5] * col[14]);
+        o[5] = col[5] + (-sy * col[6] + sx * col[7]) - (cb[6] * col[12] + cb[7] * col[13] + cb[8] * col[14]);
+        o[6] = col[6] + (cb[0] * col[9] + cb[1] * col[10] + cb[2] * col[11]);
+        o[7] = col[7] + (cb[3] * col[9] + cb[4] * col[10] + cb[5] * col[11]);
+        o[8] = col[8] + (cb[6] * col[9] + cb[7] * col[10] + cb[8] * col[11]);
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
-          P(9 + c3, j) = p.ag[c3] * col[9 + c3];
-          P(12 + c3, j) = p.aa[c3] * col[12 + c3];
+          o[9 + c3] = p.ag[c3] * col[9 + c3];
+          o[12 + c3] = p.aa[c3] * col[12 + c3];
+        }
+        if (q < 3 || m < 3) {
+#pragma unroll
+          for (int r = 0; r < kEkfN; ++r) P(r, j) = o[r];
         }
       }
-      // sweep 2, row by row: P = A Phi^T
-#pragma unroll 1
-      for (int r = 0; r < kEkfN; ++r) {
+      __syncwarp();
+      // Q of this lane's velocity and attitude rows (lanes 0..2): row q of C diag(vrw^2 dt) C^T and of
+      // C diag(arw^2 dt) C^T (C = b -> n, here cb / dt), the model-mismatch random walks on the diagonal
+      const double inv_dt2 = 1.0 / (dt * dt);
+      double qv[3], qp[3];
+      {
+        double mycb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mycb[k] = (q == 0) ? cb[k] : ((q == 1) ? cb[3 + k] : cb[6 + k]);
+        const double kv0 = mycb[0] * p.vrw2dt[0] * inv_dt2, kv1 = mycb[1] * p.vrw2dt[1] * inv_dt2,
+                     kv2 = mycb[2] * p.vrw2dt[2] * inv_dt2;
+        const double kp0 = mycb[0] * p.arw2dt[0] * inv_dt2, kp1 = mycb[1] * p.arw2dt[1] * inv_dt2,
+                     kp2 = mycb[2] * p.arw2dt[2] * inv_dt2;
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+          qv[c3] = kv0 * cb[c3 * 3] + kv1 * cb[c3 * 3 + 1] + kv2 * cb[c3 * 3 + 2];
+          qp[c3] = kp0 * cb[c3 * 3] + kp1 * cb[c3 * 3 + 1] + kp2 * cb[c3 * 3 + 2];
+        }
+      }
+      // sweep 2, this lane's rows: P = A Phi^T, + Q
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int r = ekf_own(q, m);
         double a[kEkfN];
 #pragma unroll
-        for (int q = 0; q < kEkfN; ++q) a[q] = P(r, q);
-        P(r, 0) = fma(dt, a[3], a[0]);
-        P(r, 1) = fma(dt, a[4], a[1]);
-        P(r, 2) = fma(dt, a[5], a[2]);
-        P(r, 3) = a[3] + (-sz * a[7] + sy * a[8]) - (cb[0] * a[12] + cb[1] * a[13] + cb[2] * a[14]);
-        P(r, 4) = a[4] + (sz * a[6] - sx * a[8]) - (cb[3] * a[12] + cb[4] * a[13] + cb[5] * a[14]);
-        P(r, 5) = a[5] + (-sy * a[6] + sx * a[7]) - (cb[6] * a[12] + cb[7] * a[13] + cb[8] * a[14]);
-        P(r, 6) = a[6] + (cb[0] * a[9] + cb[1] * a[10] + cb[2] * a[11]);
-        P(r, 7) = a[7] + (cb[3] * a[9] + cb[4] * a[10] + cb[5] * a[11]);
-        P(r, 8) = a[8] + (cb[6] * a[9] + cb[7] * a[10] + cb[8] * a[11]);
+        for (int c2 = 0; c2 < kEkfN; ++c2) a[c2] = P(r, c2);
+        double o[kEkfN];
+        o[0] = fma(dt, a[3], a[0]);
+        o[1] = fma(dt, a[4], a[1]);
+        o[2] = fma(dt, a[5], a[2]);
+        o[3] = a[3] + (-sz * a[7] + sy * a[8]) - (cb[0] * a[12] + cb[1] * a[13] + cb[2] * a[14]);
+        o[4] = a[4] + (sz * a[6] - sx * a[8]) - (cb[3] * a[12] + cb[4] * a[13] + cb[5] * a[14]);
+        o[5] = a[5] + (-sy * a[6] + sx * a[7]) - (cb[6] * a[12] + cb[7] * a[13] + cb[8] * a[14]);
+        o[6] = a[6] + (cb[0] * a[9] + cb[1] * a[10] + cb[2] * a[11]);
+        o[7] = a[7] + (cb[3] * a[9] + cb[4] * a[10] + cb[5] * a[11]);
+        o[8] = a[8] + (cb[6] * a[9] + cb[7] * a[10] + cb[8] * a[11]);
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
-          P(r, 9 + c3) = p.ag[c3] * a[9 + c3];
-          P(r, 12 + c3) = p.aa[c3] * a[12 + c3];
+          o[9 + c3] = p.ag[c3] * a[9 + c3];
+          o[12 + c3] = p.aa[c3] * a[12 + c3];
         }
-      }
-      // Q: C diag(vrw^2 dt) C^T and C diag(arw^2 dt) C^T (C = b -> n, here cb / dt), bias drives
-      const double inv_dt2 = 1.0 / (dt * dt);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
+        // the row's share of Q: m names the block of lanes 0..2, lane 3 holds gyro-bias row m
+        if (m < 3) o[9 + m] += (q == 3) ? p.qg[m] : 0.0;
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
-          const double qv = (cb[r * 3] * p.vrw2dt[0] * cb[c3 * 3] + cb[r * 3 + 1] * p.vrw2dt[1] * cb[c3 * 3 + 1] +
-                             cb[r * 3 + 2] * p.vrw2dt[2] * cb[c3 * 3 + 2]) * inv_dt2;
-          const double qa = (cb[r * 3] * p.arw2dt[0] * cb[c3 * 3] + cb[r * 3 + 1] * p.arw2dt[1] * cb[c3 * 3 + 1] +
-                             cb[r * 3 + 2] * p.arw2dt[2] * cb[c3 * 3 + 2]) * inv_dt2;
-          P(3 + r, 3 + c3) += qv;
-          P(6 + r, 6 + c3) += qa;
+          if (m == 1) o[3 + c3] = (q < 3) ? (o[3 + c3] + qv[c3]) + ((c3 == q) ? p.qv_extra : 0.0) : o[3 + c3];
+          if (m == 2) o[6 + c3] = (q < 3) ? (o[6 + c3] + qp[c3]) + ((c3 == q) ? p.qphi_extra : 0.0) : o[6 + c3];
+          if (m == 3) o[12 + c3] += (c3 == q) ? p.qa[c3] : 0.0;
         }
+        if (q < 3 || m < 3) {
 #pragma unroll
-      for (int c3 = 0; c3 < 3; ++c3) {
-        P(3 + c3, 3 + c3) += p.qv_extra;
-        P(6 + c3, 6 + c3) += p.qphi_extra;
-        P(9 + c3, 9 + c3) += p.qg[c3];
-        P(12 + c3, 12 + c3) += p.qa[c3];
+          for (int c2 = 0; c2 < kEkfN; ++c2) P(r, c2) = o[c2];
+        }
       }
+      __syncwarp();
     }
-    // ================= nominal state ==========================================================
+    // ================= nominal state (replicated) ===============================================
     const bool resync = ((i + 1) & (kResync - 1)) == 0;
     nav_step<0, false, 0>(st, w, f, dt, p.earth_rot != 0, 0, resync);
 #pragma unroll
@@ -391,7 +452,7 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
     }
   }
 
-  if (active) {
+  if (active && q == 0) {
     const double* r = p.ref_nav + (p.n - 1) * 9;
     double* e = p.end_err + run * 9;
     e[0] = angle_range_pi(st.yaw - r[0]);
@@ -414,7 +475,7 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const __grid_constant_
       double* o = p.consist + run * 19;
       o[0] = nees[0]; o[1] = nees[1]; o[2] = nees[2];
 #pragma unroll
-      for (int q = 0; q < kEkfN; ++q) o[3 + q] = static_cast<double>(inside[q]);
+      for (int c = 0; c < kEkfN; ++c) o[3 + c] = static_cast<double>(inside[c]);
       o[18] = static_cast<double>(epochs);
     }
   }
