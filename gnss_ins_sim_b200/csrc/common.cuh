@@ -66,6 +66,12 @@ __device__ __forceinline__ double u01_from_bits(uint32_t lo, uint32_t hi) {
   const uint32_t ml = (hi << 20) | (lo >> 12);
   return __hiloint2double(0x3FF00000u | mh, ml) - 1.0;  // [0,1)
 }
+// v = 1 + m*2^-52 in [1, 2): u_half = v - 1 and u_open0 = 2 - v, both exact
+__device__ __forceinline__ double one_plus_u01_from_bits(uint32_t lo, uint32_t hi) {
+  const uint32_t mh = hi >> 12;
+  const uint32_t ml = (hi << 20) | (lo >> 12);
+  return __hiloint2double(0x3FF00000u | mh, ml);
+}
 
 struct Normal2 {
   double z0, z1;
@@ -75,11 +81,10 @@ struct Normal2 {
 __device__ __forceinline__ Normal2 normal_pair(uint32_t t, uint32_t draw, uint32_t run_lo,
                                                uint32_t run_hi, uint32_t k0, uint32_t k1) {
   const PhiloxOut x = philox4x32_10(t, draw, run_lo, run_hi, k0, k1);
-  const double u1 = 1.0 - u01_from_bits(x.x0, x.x1);  // (0, 1]
-  const double u2 = u01_from_bits(x.x2, x.x3);        // [0, 1)
+  const double u1 = 2.0 - one_plus_u01_from_bits(x.x0, x.x1);   // 1 - u in (0, 1], exact
   const double r = sqrt_nr(-2.0 * log_unit(u1));
   double s, c;
-  sincospi_2u(2.0 * u2, &s, &c);
+  sincospi_2u(fma(one_plus_u01_from_bits(x.x2, x.x3), 2.0, -2.0), &s, &c);    // 2 u2, u2 in [0, 1), exact
   return Normal2{r * c, r * s};
 }
 

@@ -123,10 +123,13 @@ B2_HD double rcp_nr(double x) {
 #endif
 }
 
-// a / b, one ulp: q = a*y, then one residual correction
+// a / b, one ulp: q = a*y, then one residual correction.  The correction is itself quadratic in the error
+// of y, so ONE Newton step on the hardware seed (2^-22 -> 2^-44) is enough here.
 B2_HD double div_nr(double a, double b) {
 #ifdef __CUDA_ARCH__
-  const double y = rcp_nr(b);
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+  y = b2_fma(y, b2_fma(-b, y, 1.0), y);
   const double q = a * y;
   const double r = b2_fma(-b, q, a);
   return b2_fma(r, y, q);
@@ -140,11 +143,10 @@ B2_HD double sqrt_nr(double x) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  // y ~ 1/sqrt(x): two Newton steps on y, then s = x*y with one residual correction
-  double h = 0.5 * x;
-  double e = b2_fma(-h * y, y, 0.5);
-  y = b2_fma(y, e, y);
-  e = b2_fma(-h * y, y, 0.5);
+  // y ~ 1/sqrt(x): one Newton step on y (2^-22 -> 2^-43), then s = x*y with one residual correction
+  // (a Heron step: quadratic again, 2^-86 before the final rounding)
+  const double h = 0.5 * x;
+  const double e = b2_fma(-h * y, y, 0.5);
   y = b2_fma(y, e, y);
   double s = x * y;
   const double r = b2_fma(-s, s, x);
@@ -187,10 +189,9 @@ B2_HD void sincos_kernel(double r, double* s, double* c) {
   pc = b2_fma(z, pc, B2K(9, 2.48015872894767294178e-05));
   pc = b2_fma(z, pc, B2K(10, -1.38888888888741095749e-03));
   pc = b2_fma(z, pc, B2K(11, 4.16666666666666019037e-02));
-  const double hz = 0.5 * z;
-  const double w = 1.0 - hz;
-  // (1 - w) - hz is the rounding error of w; fold it back (fdlibm's trick, keeps < 1 ulp)
-  *c = w + (((1.0 - w) - hz) + z * (z * pc));
+  // two roundings near 1 (fdlibm folds the rounding error of 1 - z/2 back for < 1 ulp; this is <= 1 ulp
+  // and five operations shorter)
+  *c = b2_fma(z * z, pc, b2_fma(-0.5, z, 1.0));
 }
 
 B2_HD void quadrant_fix(int q, double sr, double cr, double* s, double* c) {
@@ -229,18 +230,13 @@ B2_HD void sincospi_2u(double x, double* s, double* c) {
   const int q = b2_lo32(t);
   const double qd = t - kMagic;
   const double r = b2_fma(-qd, 0.5, x);  // exact, |r| <= 1/4
-  // pi * r in double-double: pi = PI_hi + PI_lo
+  // pi * r rounded once: |r| <= 1/4, so the angle is off by at most 2^-53 * pi/4 (half an ulp of the
+  // result at worst; a double-double product would buy that back for five more operations)
   const double PI_hi = B2K(16, 3.14159265358979311600e+00);
-  const double PI_lo = B2K(17, 1.22464679914735317723e-16);
   const double a = r * PI_hi;
-  const double e = b2_fma(r, PI_hi, -a);        // rounding error of a
-  const double a_lo = b2_fma(r, PI_lo, e);
   double sr, cr;
   sincos_kernel(a, &sr, &cr);
-  // first-order correction for the low part: sin(a+d) = s + c d, cos(a+d) = c - s d
-  const double s2 = b2_fma(cr, a_lo, sr);
-  const double c2 = b2_fma(-sr, a_lo, cr);
-  quadrant_fix(q, s2, c2, s, c);
+  quadrant_fix(q, sr, cr, s, c);
 }
 
 // log(x) for normal x in (0, 2): fdlibm __ieee754_log without the special cases

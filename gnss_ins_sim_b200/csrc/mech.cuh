@@ -105,8 +105,10 @@ B2_DEV GeoParam geo_param_sc(double sl, double cl, double h) {
   p.rm = ((kRe * (1 - kESqr)) * inv_sq) * (inv_sq * inv_sq);
   p.rn = kRe * inv_sq;
   const double g1 = kNormalGravity * (1 + kGravK * sl_sqr) * inv_sq;
+  // (the reference divides 3 h^2 by Re twice, geoparams.py:52; one multiply by the constant 1 / Re^2
+  // differs from that by an ulp of a 1e-9 g term and keeps two divisions out of the step's chain)
   p.g = g1 * (1.0 - (2.0 / kRe) * (1.0 + kFlat + kGravM - 2.0 * kFlat * sl_sqr) * h +
-              3.0 * h * h / kRe / kRe);
+              (3.0 * h * h) * (1.0 / (kRe * kRe)));
   return p;
 }
 B2_DEV GeoParam geo_param(double lat, double h) {
