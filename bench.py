@@ -426,6 +426,12 @@ def run_b200(args):
                              'put ONE integrator warp on an SM: the serial recurrence is bound by the '
                              'dependent-issue latency of that warp (8.8 cycles per dependent DFMA, '
                              'profiles/ilp_probe_r02.jsonl), not by the pipe')
+        if 'fp64_thread_instructions_per_run_step_one_lane' in rin:
+            # the same count for ONE lane per run: the share of the issued FP64 work that is not a
+            # replica of another lane's (lane groups replicate the strapdown step)
+            fp64['fp64_inst_per_run_step_one_lane'] = rin['fp64_thread_instructions_per_run_step_one_lane']
+            fp64['frac_nonreplicated'] = (rin['fp64_thread_instructions_per_run_step_one_lane'] * k_rate
+                                          / dfma.value)
         traffic = rin.get('dram_bytes_per_launch')
     else:
         fp64['frac'] = None

@@ -11,8 +11,8 @@
 //
 // One named barrier per round of kAvRound samples couples the three stages: in interval i the
 // producers fill round i, A integrates round i-1, V round i-2 (slots triple-buffered, the ring
-// double-buffered).  A and V sit alone on SM sub-partitions 0 and 1; the producers share 2 and 3 (CTA
-// of 12 warps, the four that would land on sub-partitions 0 and 1 leave at once).
+// double-buffered).  A sits alone on SM sub-partition 0; V shares sub-partition 1 with two producers, the
+// other four share 2 and 3 (CTA of 12 warps, four of which leave at once).
 #pragma once
 #include "mc_spec_kernel.cuh"
 
@@ -40,10 +40,13 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
   __shared__ AvSmem<G> sm;
   const int lane = threadIdx.x & 31;
   const int pwarp = threadIdx.x >> 5;
-  // warps 0 (A) and 1 (V) own sub-partitions 0 and 1; producers are warps 2,3,6,7,10,11
+  // warp w runs on sub-partition w % 4.  A (warp 0) has sub-partition 0 to itself -- it is the critical
+  // path --; V (warp 1), which is idle more than half of the time, shares sub-partition 1 with two
+  // producers (warps 5, 9); the other four producers are warps 2, 6 and 3, 7; warps 4, 8, 10, 11 leave
   const bool is_a = pwarp == 0, is_v = pwarp == 1;
-  const bool is_p = (pwarp & 3) >= 2;
-  const int pp = (pwarp >> 2) * 2 + (pwarp & 1);          // producer index 0..5 = its channel
+  const bool is_p = pwarp == 2 || pwarp == 3 || pwarp == 5 || pwarp == 6 || pwarp == 7 || pwarp == 9;
+  // producer index 0..5 = its channel: warps 2 3 5 6 7 9
+  const int pp = (pwarp <= 3) ? pwarp - 2 : ((pwarp <= 7) ? pwarp - 3 : 5);
   const int j = lane % G;
   const int grp = lane / G;
   const int64_t run_raw = static_cast<int64_t>(blockIdx.x) * kRunsPerCta + grp;
@@ -102,22 +105,27 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
           mbar_wait(&sm.full[s], static_cast<uint32_t>((tile / kStagesFast) & 1));
         }
         const int buf = static_cast<int>(i % 3);
-#pragma unroll 1
+        // the Box-Muller pairs of all passes of the round first (unconditionally: a sample past the end
+        // costs nothing and is dropped): independent chains, interleaved by the scheduler
+        Normal2 z[kPasses];
+#pragma unroll
+        for (int b = 0; b < kPasses; ++b)
+          z[b] = normal_pair(static_cast<uint32_t>(tile * kTile + base + b * G + j), c, run_lo, run_hi, p.k0, p.k1);
+#pragma unroll
         for (int b = 0; b < kPasses; ++b) {
           const int tj = base + b * G + j;
           const int64_t t = tile * kTile + tj;
           const bool live = tj < cnt;
-          Normal2 z{0.0, 0.0};
+          const double z0 = live ? z[b].z0 : 0.0;
           double m = 0.0;
           if (live) {
-            z = normal_pair(static_cast<uint32_t>(t), c, run_lo, run_hi, p.k0, p.k1);
             const double ref = is_acc ? sm.accel[s][tj * 3 + ax] : sm.gyro[s][tj * 3 + ax];
-            m = (ref + e.b[ax]) + e.w[ax] * z.z1;
+            m = (ref + e.b[ax]) + e.w[ax] * z[b].z1;
             if (any_vib)
               m += vib_term(e, ax, is_acc ? 0 : 1, static_cast<uint32_t>(t), run_lo, run_hi, p.k0, p.k1, run, phase);
           }
-          const double d = gm_block<G>(e.gm_b[ax] * z.z0, e.gm_a[ax], apj, aG, j, carry);
-          m += d + e.wd[ax] * z.z0;
+          const double d = gm_block<G>(e.gm_b[ax] * z0, e.gm_a[ax], apj, aG, j, carry);
+          m += d + e.wd[ax] * z0;
           int64_t row;
           if (warp_dumps && dump && live && p.out_gyro && dump_row(p, t, &row))
             (is_acc ? p.out_accel : p.out_gyro)[run * p.osr + row * p.ost + ax * p.osc] = m;
@@ -161,8 +169,7 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
         const int sbuf = static_cast<int>((i - 1) % 3), rbuf = static_cast<int>((i - 1) & 1);
         // samples of this round that are followed by a step (the last sample of the series is not)
         const int kmax = static_cast<int>(min64(kAvRound, p.n - 1 - r0));
-#pragma unroll 1
-        for (int k = 0; k < kmax; ++k) {
+        auto a_step = [&](int k) {                        // one step with the exact path and the history rows
           const SampleSlot& sl = sm.slot[sbuf][k / G][lane - j + (k % G)];
           const Vec3 w{sl.g[0], sl.g[1], sl.g[2]};
           att_step(a, w, p.dt, ((r0 + k + 1) & (kResync - 1)) == 0);
@@ -180,6 +187,42 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
             p.out_att[o + p.osc] = a.pitch;
             p.out_att[o + 2 * p.osc] = r;
             if (p.out_quat) write_quat(p.out_quat + (run * p.dump_rows + row) * 4, y, a.pitch, r);
+          }
+        };
+        if (warp_dumps || kmax < kAvRound) {
+#pragma unroll 1
+          for (int k = 0; k < kmax; ++k) a_step(k);
+        } else {
+          // Blocks of four steps as ONE basic block without the exact-path branch (mc_spec_kernel.cuh has
+          // the same scheme): the next step's loads and rate products overlap the tail of the previous
+          // one.  A block that holds a time-based re-evaluation (1 of 16), or in which any lane needed
+          // the exact path, is (re)done step by step from the saved state; the ring is overwritten with
+          // the same or the corrected values before V sees it (V reads after the next barrier).
+#pragma unroll 1
+          for (int kb = 0; kb < kAvRound; kb += 4) {
+            bool redo = ((r0 + kb) & (kResync - 1)) + 4 >= kResync;
+            if (!redo) {
+              const AttState saved = a;
+              bool cold = false;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const SampleSlot& sl = sm.slot[sbuf][(kb + k) / G][lane - j + ((kb + k) % G)];
+                const Vec3 w{sl.g[0], sl.g[1], sl.g[2]};
+                cold |= att_step<true>(a, w, p.dt, false);
+                if (j == 0) {
+                  double* o = sm.ring[rbuf][kb + k][grp];
+                  reinterpret_cast<double2*>(o)[0] = make_double2(a.sc.sy, a.sc.cy);
+                  reinterpret_cast<double2*>(o)[1] = make_double2(a.sc.sp, a.sc.cp);
+                  reinterpret_cast<double2*>(o)[2] = make_double2(a.sc.sr, a.sc.cr);
+                }
+              }
+              redo = __any_sync(0xffffffffu, cold);
+              if (__builtin_expect(redo, 0)) a = saved;
+            }
+            if (redo) {
+#pragma unroll 1
+              for (int k = 0; k < 4; ++k) a_step(kb + k);
+            }
           }
         }
       }
@@ -222,8 +265,7 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
       const int64_t r0 = (i - 2) * kAvRound;
       const int sbuf = static_cast<int>((i - 2) % 3), rbuf = static_cast<int>((i - 2) & 1);
       const int kmax = static_cast<int>(min64(kAvRound, p.n - 1 - r0));
-#pragma unroll 1
-      for (int k = 0; k < kmax; ++k) {
+      auto v_step = [&](int k, bool hist) {
         const SampleSlot& sl = sm.slot[sbuf][k / G][lane - j + (k % G)];
         const Vec3 w{sl.g[0], sl.g[1], sl.g[2]};
         const Vec3 f{sl.a[0], sl.a[1], sl.a[2]};
@@ -234,7 +276,7 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
         vel_step(v, w, f, old, now, p.dt);
         old = now;
         int64_t row;
-        if (warp_dumps && dump && j == 0 && p.out_att && dump_row(p, r0 + k + 1, &row)) {
+        if (hist && dump && j == 0 && p.out_att && dump_row(p, r0 + k + 1, &row)) {
           const int64_t oo = run * p.osr + row * p.ost;
           p.out_pos[oo] = v.pos.x;
           p.out_pos[oo + p.osc] = v.pos.y;
@@ -242,6 +284,16 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
           p.out_vel[oo] = v.vel.x;
           p.out_vel[oo + p.osc] = v.vel.y;
           p.out_vel[oo + 2 * p.osc] = v.vel.z;
+        }
+      };
+      if (warp_dumps || kmax < kAvRound) {
+#pragma unroll 1
+        for (int k = 0; k < kmax; ++k) v_step(k, true);
+      } else {
+#pragma unroll 1
+        for (int kb = 0; kb < kAvRound; kb += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v_step(kb + k, false);
         }
       }
     }

@@ -33,6 +33,9 @@ struct SpecShape {
   static constexpr bool kSpare = (P == 6 && WI == 1);
   static constexpr int kThreads = (WI * (1 + P) + (kSpare ? 1 : 0)) * 32;
   static constexpr int kChan = 6 / P;                 // channels per producer warp
+  // speculative straight-line blocks (see the integrator loop): groups of 4 and 8 lanes, the shapes of
+  // the few-runs configurations, which run without a register cap
+  static constexpr int kSpecBlock = (G == 4 || G == 8) ? 4 : 0;
   static_assert(6 % P == 0 && kTile % kRound == 0 && 32 % G == 0, "shape");
 };
 
@@ -41,6 +44,8 @@ struct SpecSmem {
   alignas(128) double gyro[kStagesFast][kTile * 3];
   alignas(128) double accel[kStagesFast][kTile * 3];
   alignas(16) SampleSlot slot[2][SpecShape<G, P, WI>::kPasses][WI][32];
+  // the state before a speculative block (integrator lanes; one dummy element where there are none)
+  alignas(16) NavState saved[SpecShape<G, P, WI>::kSpecBlock ? WI : 1][SpecShape<G, P, WI>::kSpecBlock ? 32 : 1];
   alignas(8) uint64_t full[kStagesFast];
   alignas(8) uint64_t empty[kStagesFast];
 };
@@ -71,6 +76,7 @@ mc_spec_kernel(const __grid_constant__ McParams p) {
   __shared__ SpecSmem<G, P, WI> sm;
   constexpr int kRunsPerWarp = 32 / G;
   constexpr int kChan = Sh::kChan;
+  constexpr int kSpecBlock = Sh::kSpecBlock;
   const int lane = threadIdx.x & 31;
   const int pwarp = threadIdx.x >> 5;
   const bool integrator = pwarp < WI;
@@ -146,40 +152,52 @@ mc_spec_kernel(const __grid_constant__ McParams p) {
 #ifdef B2INS_PHASE_CLOCKS
         if (p.debug & 1) { group_sync(); continue; }   // isolate the integrator
 #endif
+        // two passes at a time, the Box-Muller pairs of both (and of all channels) first --
+        // unconditionally: a sample past the end costs nothing and is dropped --: independent chains
+        // the scheduler interleaves
+        constexpr int kIlp = (G >= 4 && Sh::kPasses >= 2) ? 2 : 1;     // (narrow groups run under a register cap)
 #pragma unroll 1
-        for (int b = 0; b < Sh::kPasses; ++b) {
-          const int tj = base + b * G + j;
-          const int64_t t = t0 + tj;
-          const bool live = tj < cnt;
-          SampleSlot& mine = sm.slot[buf][b][gi][lane];
-          // the Box-Muller pairs of all channels first: independent chains the scheduler interleaves
-          Normal2 z[kChan];
+        for (int b0 = 0; b0 < Sh::kPasses; b0 += kIlp) {
+          Normal2 z[kIlp][kChan];
 #pragma unroll
-          for (int q = 0; q < kChan; ++q) {
-            z[q] = Normal2{0.0, 0.0};
-            if (live) z[q] = normal_pair(static_cast<uint32_t>(t), pp * kChan + q, run_lo, run_hi, p.k0, p.k1);
-          }
+          for (int bi = 0; bi < kIlp; ++bi)
 #pragma unroll
-          for (int q = 0; q < kChan; ++q) {
-            const int c = pp * kChan + q;
-            const int ax = c % 3;
-            const bool is_acc = c < 3;
-            const TriadNoise& e = is_acc ? p.accel : p.gyro;
-            double m = 0.0;
-            if (live) {
-              const double ref = is_acc ? sm.accel[s][tj * 3 + ax] : sm.gyro[s][tj * 3 + ax];
-              m = (ref + e.b[ax]) + e.w[ax] * z[q].z1;
-              if (any_vib)
-                m += vib_term(e, ax, is_acc ? 0 : 1, static_cast<uint32_t>(t), run_lo, run_hi, p.k0, p.k1,
-                              run, phase);
+            for (int q = 0; q < kChan; ++q) {
+              z[bi][q] = Normal2{0.0, 0.0};
+              if (kIlp > 1 || base + (b0 + bi) * G + j < cnt)
+                z[bi][q] = normal_pair(static_cast<uint32_t>(t0 + base + (b0 + bi) * G + j), pp * kChan + q, run_lo,
+                                       run_hi, p.k0, p.k1);
             }
-            // + drift: the GM state d[t] (pathgen.py:583-590) or drift*z[t] if tau = inf (:591-593)
-            const double d = gm_block<G>(e.gm_b[ax] * z[q].z0, e.gm_a[ax], apj[q], aG[q], j, carry[q]);
-            m += d + e.wd[ax] * z[q].z0;
-            int64_t row;
-            if (warp_dumps && dump && live && p.out_gyro && dump_row(p, t, &row))
-              (is_acc ? p.out_accel : p.out_gyro)[run * p.osr + row * p.ost + ax * p.osc] = m;
-            if (is_acc) mine.a[ax] = m; else mine.g[ax] = m;
+#pragma unroll
+          for (int bi = 0; bi < kIlp; ++bi) {
+            const int b = b0 + bi;
+            const int tj = base + b * G + j;
+            const int64_t t = t0 + tj;
+            const bool live = tj < cnt;
+            SampleSlot& mine = sm.slot[buf][b][gi][lane];
+#pragma unroll
+            for (int q = 0; q < kChan; ++q) {
+              const int c = pp * kChan + q;
+              const int ax = c % 3;
+              const bool is_acc = c < 3;
+              const TriadNoise& e = is_acc ? p.accel : p.gyro;
+              const double z0 = (kIlp > 1 && !live) ? 0.0 : z[bi][q].z0;
+              double m = 0.0;
+              if (live) {
+                const double ref = is_acc ? sm.accel[s][tj * 3 + ax] : sm.gyro[s][tj * 3 + ax];
+                m = (ref + e.b[ax]) + e.w[ax] * z[bi][q].z1;
+                if (any_vib)
+                  m += vib_term(e, ax, is_acc ? 0 : 1, static_cast<uint32_t>(t), run_lo, run_hi, p.k0, p.k1,
+                                run, phase);
+              }
+              // + drift: the GM state d[t] (pathgen.py:583-590) or drift*z[t] if tau = inf (:591-593)
+              const double d = gm_block<G>(e.gm_b[ax] * z0, e.gm_a[ax], apj[q], aG[q], j, carry[q]);
+              m += d + e.wd[ax] * z0;
+              int64_t row;
+              if (warp_dumps && dump && live && p.out_gyro && dump_row(p, t, &row))
+                (is_acc ? p.out_accel : p.out_gyro)[run * p.osr + row * p.ost + ax * p.osc] = m;
+              if (is_acc) mine.a[ax] = m; else mine.g[ax] = m;
+            }
           }
         }
         B2_CLK(cp1);
@@ -267,6 +285,33 @@ mc_spec_kernel(const __grid_constant__ McParams p) {
           }
         } else if (G == 1) {
           if (kmax > 0) one_step(0, false);
+        } else if (kSpecBlock > 0 && kmax == G) {
+          // Blocks of four steps as ONE basic block, no exact-path branch inside -- the next step's loads
+          // and rate products overlap the tail of the previous one -- unless the block holds a time-based
+          // re-evaluation (1 of 16).  If any lane needed the exact path (rare: an increment above
+          // kRotMax, a pitch reflection, a NaN) the warp restores the saved state and redoes the block
+          // step by step; every step computes the same numbers either way.
+#pragma unroll 1
+          for (int kb = 0; kb < G; kb += kSpecBlock) {
+            bool redo = (((t0 + pb + kb) & (kResync - 1)) + kSpecBlock >= kResync);
+            if (!redo) {
+              sm.saved[gi][lane] = st;
+              bool cold = false;
+#pragma unroll
+              for (int k = 0; k < kSpecBlock; ++k) {
+                const SampleSlot& sl = grp[kb + k];
+                const Vec3 w{sl.g[0], sl.g[1], sl.g[2]};
+                const Vec3 f{sl.a[0], sl.a[1], sl.a[2]};
+                cold |= nav_step<RF, SPLIT, 0, true>(st, w, f, p.dt, p.earth_rot != 0, role, false);
+              }
+              redo = __any_sync(0xffffffffu, cold);
+              if (__builtin_expect(redo, 0)) st = sm.saved[gi][lane];
+            }
+            if (redo) {
+#pragma unroll 1
+              for (int k = 0; k < kSpecBlock; ++k) one_step(kb + k, false);
+            }
+          }
         } else {
           // two steps per iteration: the off-chain tail of step k overlaps the chain of step k + 1
           int k = 0;

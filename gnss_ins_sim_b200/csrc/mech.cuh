@@ -281,8 +281,12 @@ B2_DEV void resync_exact(NavState& s) {
 // the reciprocal cosine (times dt) kept with the state so that no division sits on the yaw/roll chain.
 // ODO: 0 = free integration, 1 = odometer variant (compile-time: no branch inside the step's basic
 // block), 2 = decided by odo_rt at run time
-template <int RF, bool SPLIT, int ODO = 0>
-B2_DEV void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel, double dt, bool earth_rot, int role,
+// SPEC (speculative): the step WITHOUT the exact-path branch -- straight-line code, so that several steps
+// unroll into one basic block and the scheduler overlaps them.  Returns whether the exact path was due
+// (an increment above kRotMax, a pitch reflection, a NaN); the caller then restores the state it saved
+// and redoes the steps with SPEC = false.  (SPEC = false returns the same flag, already handled.)
+template <int RF, bool SPLIT, int ODO = 0, bool SPEC = false>
+B2_DEV bool nav_step(NavState& s, const Vec3& gyro, const Vec3& accel, double dt, bool earth_rot, int role,
                      bool resync, bool odo_rt = false) {
   const bool odo = (ODO == 2) ? odo_rt : (ODO == 1);
   const Vec3 vel_old = s.vel;
@@ -357,7 +361,9 @@ B2_DEV void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel, double dt
     }
 #endif
   }
-  if (__builtin_expect(cold, 0)) resync_exact<RF>(s);
+  if (!SPEC) {
+    if (__builtin_expect(cold, 0)) resync_exact<RF>(s);
+  }
   s.icp = rcp_nr(s.sc.cp) * dt;
   // ---- velocity, position ------------------------------------------------------------------
   if (RF == 1) {
@@ -382,6 +388,7 @@ B2_DEV void nav_step(NavState& s, const Vec3& gyro, const Vec3& accel, double dt
     }
     // vel_b[i] = c_bn(i).dot(vel[i]) (:172) is not an output of the plugin; not computed
   }
+  return cold;
 }
 
 // ---- ref_frame 1, the step split in two (mc_av_kernel.cuh) ------------------------------------------
@@ -395,7 +402,9 @@ struct AttState {
 };
 
 // attitude.euler_update_zyx + euler2dcm's sin/cos for the new angles: the attitude half of nav_step<1>
-B2_DEV void att_step(AttState& s, const Vec3& w, double dt, bool resync) {
+// SPEC: without the exact-path branch, returns whether it was due (see nav_step)
+template <bool SPEC = false>
+B2_DEV bool att_step(AttState& s, const Vec3& w, double dt, bool resync) {
   const double t = b2_fma(w.z, s.sc.cr, w.y * s.sc.sr);
   const double dy = t * s.icp;
   const double dp = b2_fma(w.y, s.sc.cr, -(w.z * s.sc.sr)) * dt;
@@ -408,7 +417,7 @@ B2_DEV void att_step(AttState& s, const Vec3& w, double dt, bool resync) {
   rot_small(s.sc.sy, s.sc.cy, dy);
   rot_small(s.sc.sp, s.sc.cp, dp);
   rot_small(s.sc.sr, s.sc.cr, dr);
-  if (__builtin_expect(cold, 0)) {
+  if (!SPEC && __builtin_expect(cold, 0)) {
     NavState n;            // the exact path works on the full state type
     n.yaw = s.yaw; n.pitch = s.pitch; n.roll = s.roll;
     n.pos = Vec3{0.0, 0.0, 0.0};
@@ -417,6 +426,7 @@ B2_DEV void att_step(AttState& s, const Vec3& w, double dt, bool resync) {
     s.sc = n.sc;
   }
   s.icp = rcp_nr(s.sc.cp) * dt;
+  return cold;
 }
 
 struct VelState {
