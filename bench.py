@@ -324,7 +324,7 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     lanes_used = args.lanes or lib.b2ins_diag_auto_lanes(R, 1, sms)
-    shape_used = _lib.mc_shape(lanes_used)
+    shape_used = _lib.mc_shape(lanes_used, 1)
 
     merger = p2p = None
     exchange = 'none'
@@ -423,7 +423,7 @@ def run_b200(args):
         fp64['fp64_inst_per_run_step'] = rin['fp64_thread_instructions_per_run_step']
         fp64['frac'] = rin['fp64_thread_instructions_per_run_step'] * k_rate / dfma.value
         fp64['frac_note'] = ('FP64 thread-instructions issued / measured FP64-FMA issue rate.  1000 runs '
-                             'put ONE integrator warp on an SM: the serial recurrence is bound by the '
+                             'put ONE attitude warp on an SM: the serial recurrence is bound by the '
                              'dependent-issue latency of that warp (8.8 cycles per dependent DFMA, '
                              'profiles/ilp_probe_r02.jsonl), not by the pipe')
         if 'fp64_thread_instructions_per_run_step_one_lane' in rin:
@@ -505,12 +505,12 @@ def run_b200(args):
                           'd2h_bytes_per_step': d2h + R * n * 72,
                           'api': 'Sim.run + get_error_stats + Sim.histories(): att/pos/vel of every run '
                                  '([R, n, 3] x 3, what the reference Sim.run leaves in its data manager)'},
-        # per step: mc_spec_kernel + stats_small_kernel (N = 1) / stats_exchange_kernel (N > 1)
+        # per step: the K12 kernel + stats_small_kernel (N = 1) / stats_exchange_kernel (N > 1)
         'gpu_launches': args.steps * 2,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': traffic,
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
-                     'kernel': 'mc_spec_kernel (K12)', 'kernel_ms': k_ms,
+                     'kernel': 'mc_av_kernel (K12, attitude / velocity split form)' if shape_used == '6,2,0' else 'mc_spec_kernel (K12)', 'kernel_ms': k_ms,
                      'algorithmic_bytes_per_launch': alg_bytes,
                      'note': 'K12 reads the shared trajectory once and writes 72 B per run: it is bound '
                              'by FP64 issue / dependent-issue latency, not by HBM; see roofline_fp64'},

@@ -96,7 +96,7 @@ SIGNATURES = {
     'b2ins_ins_loose_f64': (_I, [ctypes.POINTER(EkfConfig)] + [_P] * 15),
     'b2ins_diag_dfma_rate': (_I, [c_double_p]),
     'b2ins_diag_auto_lanes': (_I, [_L, _I, _I]),
-    'b2ins_diag_mc_shape': (_I, [_I, ctypes.POINTER(ctypes.c_int)]),
+    'b2ins_diag_mc_shape': (_I, [_I, _I, ctypes.POINTER(ctypes.c_int)]),
 }
 
 _lib = None
@@ -130,10 +130,11 @@ def load():
     return lib
 
 
-def mc_shape(lanes):
-    """'P,WI,split' of the fused Monte-Carlo launch for a lane-group width ('0' = single-warp form)."""
+def mc_shape(lanes, ref_frame=1):
+    """'P,WI,split' of the fused Monte-Carlo launch for a lane-group width and a reference frame
+    ('0' = single-warp form)."""
     out = (ctypes.c_int * 3)()
-    check(load().b2ins_diag_mc_shape(int(lanes), out))
+    check(load().b2ins_diag_mc_shape(int(lanes), int(ref_frame), out))
     return '%d,%d,%d' % (out[0], out[1], out[2]) if out[0] else '0'
 
 

@@ -19,8 +19,21 @@
 namespace b2ins {
 
 constexpr int kAvRound = 8;
-constexpr int kAvWarps = 12;
-constexpr int kAvSync = 32 * 8;          // A + V + six producers
+// A producer warp always works on four runs x the eight samples of a round (one Box-Muller pass per round,
+// its own Gauss-Markov carry): six of them with groups of 8 lanes (four runs per CTA), twelve with groups
+// of 4 (eight runs per CTA: two producers per channel, one for each half of the runs).
+template <int G>
+struct AvShape {
+  static constexpr int kHalves = (32 / G) / 4;
+  static constexpr int kProd = 6 * kHalves;
+  static constexpr int kWarps = (G == 4) ? 16 : 12;
+  static constexpr int kSync = 32 * (2 + kProd);      // A + V + producers
+};
+// role of warp w (it runs on sub-partition w % 4): -1 = A, -2 = V, -3 = leaves at once, else producer index.
+// A (warp 0) is the critical path: alone on sub-partition 0 with groups of 8, with ONE producer (warp 4)
+// with groups of 4; V, idle more than half of the time, shares sub-partition 1 with two / three producers.
+__device__ constexpr int kAvRole8[12] = {-1, -2, 0, 1, -3, 2, 3, 4, -3, 5, -3, -3};
+__device__ constexpr int kAvRole4[16] = {-1, -2, 0, 1, 2, 3, 4, 5, -3, 6, 7, 8, -3, 9, 10, 11};
 
 template <int G>
 struct AvSmem {
@@ -33,22 +46,20 @@ struct AvSmem {
 };
 
 template <int G>
-__global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_constant__ McParams p) {
+__global__ void __launch_bounds__(AvShape<G>::kWarps * 32, 1) mc_av_kernel(const __grid_constant__ McParams p) {
   static_assert(G == 4 || G == 8, "groups of 4 or 8 lanes");
-  constexpr int kPasses = kAvRound / G;
   constexpr int kRunsPerCta = 32 / G;
+  constexpr int kProd = AvShape<G>::kProd;
+  constexpr int kAvSync = AvShape<G>::kSync;
   __shared__ AvSmem<G> sm;
   const int lane = threadIdx.x & 31;
   const int pwarp = threadIdx.x >> 5;
-  // warp w runs on sub-partition w % 4.  A (warp 0) has sub-partition 0 to itself -- it is the critical
-  // path --; V (warp 1), which is idle more than half of the time, shares sub-partition 1 with two
-  // producers (warps 5, 9); the other four producers are warps 2, 6 and 3, 7; warps 4, 8, 10, 11 leave
-  const bool is_a = pwarp == 0, is_v = pwarp == 1;
-  const bool is_p = pwarp == 2 || pwarp == 3 || pwarp == 5 || pwarp == 6 || pwarp == 7 || pwarp == 9;
-  // producer index 0..5 = its channel: warps 2 3 5 6 7 9
-  const int pp = (pwarp <= 3) ? pwarp - 2 : ((pwarp <= 7) ? pwarp - 3 : 5);
-  const int j = lane % G;
-  const int grp = lane / G;
+  const int role_w = (G == 4) ? kAvRole4[pwarp] : kAvRole8[pwarp];
+  const bool is_a = role_w == -1, is_v = role_w == -2, is_p = role_w >= 0;
+  const int pp = is_p ? role_w : 0;                        // producer index: channel pp % 6, run half pp / 6
+  // A and V: G lanes per run.  Producers: eight lanes per run (the samples of a round), four runs.
+  const int j = is_p ? (lane & 7) : lane % G;
+  const int grp = is_p ? (pp / 6) * 4 + (lane >> 3) : lane / G;      // run within the CTA
   const int64_t run_raw = static_cast<int64_t>(blockIdx.x) * kRunsPerCta + grp;
   const bool active = run_raw < p.runs;
   const int64_t run = active ? run_raw : p.runs - 1;
@@ -63,7 +74,7 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStagesFast; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 6);
+      mbar_init(&sm.empty[s], kProd);
     }
     mbar_fence_init();
   }
@@ -76,11 +87,11 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
     // =============================== producer: channel pp =========================================
     if (threadIdx.x == issuer)
       for (int s = 0; s < kStagesFast && s < num_tiles; ++s) spec_issue_tile(sm, p, s, s);
-    const int c = pp, ax = c % 3;
+    const int c = pp % 6, ax = c % 3;
     const bool is_acc = c < 3;
     const TriadNoise& e = is_acc ? p.accel : p.gyro;
     double carry = 0.0;
-    const double apj = ipow(e.gm_a[ax], j), aG = ipow(e.gm_a[ax], G);
+    const double apj = ipow(e.gm_a[ax], j), aG = ipow(e.gm_a[ax], kAvRound);
     double phase[3] = {0.0, 0.0, 0.0};
     if (p.gyro.vib_type == 2) {
 #pragma unroll
@@ -105,31 +116,26 @@ __global__ void __launch_bounds__(kAvWarps * 32, 1) mc_av_kernel(const __grid_co
           mbar_wait(&sm.full[s], static_cast<uint32_t>((tile / kStagesFast) & 1));
         }
         const int buf = static_cast<int>(i % 3);
-        // the Box-Muller pairs of all passes of the round first (unconditionally: a sample past the end
-        // costs nothing and is dropped): independent chains, interleaved by the scheduler
-        Normal2 z[kPasses];
-#pragma unroll
-        for (int b = 0; b < kPasses; ++b)
-          z[b] = normal_pair(static_cast<uint32_t>(tile * kTile + base + b * G + j), c, run_lo, run_hi, p.k0, p.k1);
-#pragma unroll
-        for (int b = 0; b < kPasses; ++b) {
-          const int tj = base + b * G + j;
+        {
+          const int tj = base + j;
           const int64_t t = tile * kTile + tj;
           const bool live = tj < cnt;
-          const double z0 = live ? z[b].z0 : 0.0;
+          Normal2 z{0.0, 0.0};
           double m = 0.0;
           if (live) {
+            z = normal_pair(static_cast<uint32_t>(t), c, run_lo, run_hi, p.k0, p.k1);
             const double ref = is_acc ? sm.accel[s][tj * 3 + ax] : sm.gyro[s][tj * 3 + ax];
-            m = (ref + e.b[ax]) + e.w[ax] * z[b].z1;
+            m = (ref + e.b[ax]) + e.w[ax] * z.z1;
             if (any_vib)
               m += vib_term(e, ax, is_acc ? 0 : 1, static_cast<uint32_t>(t), run_lo, run_hi, p.k0, p.k1, run, phase);
           }
-          const double d = gm_block<G>(e.gm_b[ax] * z0, e.gm_a[ax], apj, aG, j, carry);
-          m += d + e.wd[ax] * z0;
+          const double d = gm_block<kAvRound>(e.gm_b[ax] * z.z0, e.gm_a[ax], apj, aG, j, carry);
+          m += d + e.wd[ax] * z.z0;
           int64_t row;
           if (warp_dumps && dump && live && p.out_gyro && dump_row(p, t, &row))
             (is_acc ? p.out_accel : p.out_gyro)[run * p.osr + row * p.ost + ax * p.osc] = m;
-          SampleSlot& mine = sm.slot[buf][b][lane];
+          // sample j of run grp, where the consumers (G lanes per run, passes of G samples) look for it
+          SampleSlot& mine = sm.slot[buf][j / G][grp * G + (j % G)];
           if (is_acc) mine.a[ax] = m; else mine.g[ax] = m;
         }
         if (base + kAvRound >= cnt) {                      // last round of the tile: release the stage

@@ -23,7 +23,7 @@ template <int G>
 void launch_av(const McParams& p, cudaStream_t s) {
   const int64_t runs_per_cta = 32 / G;
   const unsigned grid = static_cast<unsigned>((p.runs + runs_per_cta - 1) / runs_per_cta);
-  mc_av_kernel<G><<<grid, kAvWarps * 32, 0, s>>>(p);
+  mc_av_kernel<G><<<grid, AvShape<G>::kWarps * 32, 0, s>>>(p);
 }
 #endif
 

@@ -378,11 +378,12 @@ int b2ins_diag_dfma_rate(double* dfma_per_s);
  * process statistics.  A pure function of its arguments: usable without a GPU. */
 int b2ins_diag_auto_lanes(int64_t runs, int fused, int sm_count);
 
-/* The launch shape of the fused, warp-specialised Monte-Carlo kernel for a lane-group width:
- * shape3[0] = producer warps per integrator warp, [1] = integrator warps per CTA, [2] = 1 if the
- * lanes of a group share the trigonometry of a step (0 for the single-warp form: all zero).
+/* The launch shape of the fused, warp-specialised Monte-Carlo kernel for a lane-group width and a
+ * reference frame: shape3[0] = producer warps per integrator warp (per channel for the split form),
+ * [1] = integrator warps per CTA (2: the step split over an attitude and a velocity warp, ref_frame 1),
+ * [2] = 1 if the lanes of a group share the trigonometry of a step (0 for the single-warp form: all zero).
  * Honours the tools' B2INS_MC_SHAPE override, i.e. reports what a launch would use.  Pure host logic. */
-int b2ins_diag_mc_shape(int lanes_per_run, int* shape3);
+int b2ins_diag_mc_shape(int lanes_per_run, int ref_frame, int* shape3);
 
 #ifdef __cplusplus
 }

@@ -443,6 +443,6 @@ def test_lanes_per_run_choice():
         [8, 8, 8, 4, 4, 4, 2, 2, 2, 2, 1, 1]
     assert pick(40001, 1) == 1 and pick(10 ** 6, 1) == 1
     assert [pick(r, 0) for r in (500, 1000, 2000, 4000, 10000, 20000, 10 ** 6)] == [32, 16, 8, 4, 2, 1, 1]
-    assert _lib.mc_shape(4) == '6,1,0' and _lib.mc_shape(32) == '1,4,1'
+    assert _lib.mc_shape(4, 0) == '6,1,0' and _lib.mc_shape(4, 1) == '6,2,0' and _lib.mc_shape(32) == '1,4,1'
     # every choice is a width the kernels are instantiated for
     assert all(pick(r, f) in (1, 2, 4, 8, 16, 32) for r in range(1, 60000, 997) for f in (0, 1))

@@ -14,9 +14,9 @@ for spec in "k1:imu_noise_kernel:6.5536e7" "k3:err_stage1_kernel:1e6" "k5:psd_ff
   tail -1 gpurun_out/ncu_r02_$mode.log
 done
 # the dominant kernel at bench.py's own workload (config 2) -> the inputs of bench.py's roofline fields
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:mc_spec_kernel -s 4 -c 1 -f \
+timeout 300 ncu --set full --import-source on --clock-control none -k 'regex:mc_(spec|av)_kernel' -s 4 -c 1 -f \
     -o gpurun_out/prof_r02_mc_c2 python bench.py --steps 3 --warmup 3 --quick > gpurun_out/ncu_r02_mc_c2.log 2>&1
-python tools/ncu_summary.py gpurun_out/prof_r02_mc_c2.ncu-rep --units 1e6 > gpurun_out/ncu_mc_spec_r02_cfg2_g4_p6.json 2>> gpurun_out/ncu_r02_mc_c2.log
+python tools/ncu_summary.py gpurun_out/prof_r02_mc_c2.ncu-rep --units 1e6 > gpurun_out/ncu_mc_r02_cfg2.json 2>> gpurun_out/ncu_r02_mc_c2.log
 rm -f gpurun_out/prof_r02_mc_c2.ncu-rep
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv \
     python bench.py --steps 2 --warmup 3 --no-config4 --c3-runs 2000 --c5-runs 512 > gpurun_out/launches_r02_bench.log 2>&1
