@@ -98,22 +98,21 @@ struct alignas(16) SampleSlot {
   double g[3], a[3];
 };
 
-// SPEC (warp-specialised kernel): two sets of slots, one being filled while the other is consumed
-template <bool PROC, bool SPEC = false>
+template <bool PROC>
 struct TileSmem {
   static constexpr int kStages = Stages<PROC>::value;
   alignas(128) double gyro[kStages][kTile * 3];
   alignas(128) double accel[kStages][kTile * 3];
   alignas(128) double nav[kStages][PROC ? kTile * 9 : 2];  // only staged for process statistics
-  alignas(16) SampleSlot slot[SPEC ? 2 : 1][kWarps][32];
+  alignas(16) SampleSlot slot[kWarps][32];
   alignas(8) uint64_t full[kStages];
   alignas(8) uint64_t empty[kStages];
 };
 
 // Issue the copies of one tile: the 16-byte-multiple part by bulk async copy (TMA)
 // completing on full[s]; an odd sample count leaves one 8-byte tail copied by hand.
-template <bool FED, bool PROC, bool SPEC>
-__device__ __forceinline__ void issue_tile(TileSmem<PROC, SPEC>& sm, const McParams& p, int64_t tile, int s) {
+template <bool FED, bool PROC>
+__device__ __forceinline__ void issue_tile(TileSmem<PROC>& sm, const McParams& p, int64_t tile, int s) {
   const int64_t t0 = tile * kTile;
   const uint32_t cnt = static_cast<uint32_t>(min64(kTile, p.n - t0));
   uint32_t tx = 0;
@@ -295,26 +294,15 @@ struct MinBlocks {
   static constexpr int value = (G == 1) ? B2INS_G1_MINBLOCKS : (G == 2 ? 3 : 2);
 };
 
-// SPEC: the warp-specialised form for lane groups of 4 and more and few runs (one warp per SM
-// sub-partition, the serial step latency-bound with two thirds of its issue slots empty).  The
-// CTA has 2 x kWarps warps: warp w < kWarps PRODUCES the samples of block b+1 (noise, Gauss-Markov
-// scan: the time-parallel part) into one set of slots while warp w + kWarps INTEGRATES block b from
-// the other set; the pair meets at a 64-thread named barrier once per block.  Both sit on the same
-// scheduler, so the producer fills the integrator's stalls.
-template <int G, int RF, bool FED, bool PROC, bool SPEC = false>
-__global__ void __launch_bounds__(SPEC ? 2 * kThreads : kThreads, SPEC ? 1 : MinBlocks<G>::value)
+// (The warp-specialised forms of the fused launch are mc_spec_kernel.cuh and mc_av_kernel.cuh.)
+template <int G, int RF, bool FED, bool PROC>
+__global__ void __launch_bounds__(kThreads, MinBlocks<G>::value)
 mc_kernel(const __grid_constant__ McParams p) {
-  static_assert(!SPEC || (G > 1 && !FED && !PROC), "specialised form: fused noise, wide groups, end-point statistics");
-  __shared__ TileSmem<PROC, SPEC> sm;
+  __shared__ TileSmem<PROC> sm;
   constexpr int kRunsPerWarp = 32 / G;
   constexpr bool kSplit = (G >= 4);
   const int lane = threadIdx.x & 31;
-  const int pwarp = threadIdx.x >> 5;                  // physical warp
-  const int warp = SPEC ? (pwarp & (kWarps - 1)) : pwarp;   // the lane groups it works for
-  const bool producer = SPEC && pwarp < kWarps;        // phase A only
-  const bool consumer = !SPEC || !producer;            // phase B, results
-  const bool prepares = !SPEC || producer;
-  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + warp) : "memory"); };
+  const int warp = threadIdx.x >> 5;
   const int j = lane % G;
   const int role = lane & 3;
   const int64_t run_raw =
@@ -340,7 +328,7 @@ mc_kernel(const __grid_constant__ McParams p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int s = 0; s < kStages && s < num_tiles; ++s) issue_tile<FED, PROC, SPEC>(sm, p, s, s);
+      for (int s = 0; s < kStages && s < num_tiles; ++s) issue_tile<FED, PROC>(sm, p, s, s);
     }
   }
 
@@ -368,7 +356,7 @@ mc_kernel(const __grid_constant__ McParams p) {
     for (int c = 0; c < 3; ++c)  // np.random.rand(1)*2*pi, pathgen.py:553-555
       phase[c] = (uniform01(0xFFFFFFFFu, kDrawPhase + c, run_lo, run_hi, p.k0, p.k1) * 2.0) * kPi;
   }
-  if (dump && j == 0 && p.out_att && consumer) {
+  if (dump && j == 0 && p.out_att) {
     const int64_t o = run * p.osr;
     p.out_att[o] = st.yaw;
     p.out_att[o + p.osc] = st.pitch;
@@ -390,19 +378,18 @@ mc_kernel(const __grid_constant__ McParams p) {
   }
 
   // ---- time loop ---------------------------------------------------------
-  int blk = 0;   // blocks of G samples so far (selects the set of slots in the specialised form)
   for (int64_t tile = 0; tile < num_tiles; ++tile) {
     const int s = static_cast<int>(tile % kStages);
     const uint32_t parity = static_cast<uint32_t>((tile / kStages) & 1);
     const int64_t t0 = tile * kTile;
     const int cnt = static_cast<int>(min64(kTile, p.n - t0));
-    if (kStaged && prepares) {   // (the integrating warps of the specialised form read no tiles)
+    if (kStaged) {
       // refill the stage the PREVIOUS tile used (all warps have had a whole tile to release
-      // it, so the producer thread hardly ever waits), then wait for this tile's data
+      // it, so the issuing thread hardly ever waits), then wait for this tile's data
       if (threadIdx.x == 0 && tile >= 1 && tile - 1 + kStages < num_tiles) {
         const int sp = static_cast<int>((tile - 1) % kStages);
         mbar_wait(&sm.empty[sp], static_cast<uint32_t>(((tile - 1) / kStages) & 1));
-        issue_tile<FED, PROC, SPEC>(sm, p, tile - 1 + kStages, sp);
+        issue_tile<FED, PROC>(sm, p, tile - 1 + kStages, sp);
       }
       B2_CLK(cw0);
       mbar_wait(&sm.full[s], parity);
@@ -410,15 +397,14 @@ mc_kernel(const __grid_constant__ McParams p) {
       B2_ACC(0, cw0, cw1);
     }
 
-    for (int base = 0; base < cnt; base += G, ++blk) {
+    for (int base = 0; base < cnt; base += G) {
       B2_CLK(ca0);
       // ---------------- phase A: lane j prepares sample t0 + base + j --------------
       double mg[3], ma[3];  // the complete measurement of sample base + j
       double mo = 0.0;      // odometer measurement (algo 1)
       const int tj = base + j;
       const int64_t t = t0 + tj;
-      const int buf = SPEC ? (blk & 1) : 0;
-      if (prepares) {
+      {
       if (FED) {
         if (tj < cnt) {
           const int64_t o = run * p.sr + t * p.st;
@@ -474,15 +460,13 @@ mc_kernel(const __grid_constant__ McParams p) {
         ma[1] = ma[2] = 0.0;
       }
       if (G > 1) {
-        SampleSlot& mine = sm.slot[buf][warp][lane];
+        SampleSlot& mine = sm.slot[warp][lane];
         mine.g[0] = mg[0]; mine.g[1] = mg[1]; mine.g[2] = mg[2];
         mine.a[0] = ma[0]; mine.a[1] = ma[1]; mine.a[2] = ma[2];
       }
-      }   // prepares
-      // hand-over: the specialised pair meets once per block (the producer then fills the other
-      // set of slots while this one is integrated); one warp doing both only needs its own lanes
-      if (SPEC) pair_sync(); else if (G > 1) __syncwarp();
-      if (!consumer) continue;
+      }
+      // hand-over from phase A to phase B: one warp doing both only needs its own lanes
+      if (G > 1) __syncwarp();
 
       B2_CLK(cb0);
       B2_ACC(2, ca0, cb0);
@@ -492,7 +476,7 @@ mc_kernel(const __grid_constant__ McParams p) {
       for (int c = 0; c < 9; ++c) keep[c] = 0.0;
       // samples of this block that are followed by a step (the last sample of the series is not)
       const int kmax = static_cast<int>(min64(min64(G, cnt - base), p.n - 1 - (t0 + base)));
-      const SampleSlot* grp = &sm.slot[buf][warp][lane - j];
+      const SampleSlot* grp = &sm.slot[warp][lane - j];
       // One step of the recurrence; HIST keeps the state after sample base+k in lane k.
       auto one_step = [&](int k, bool hist) {
         Vec3 w, f;
@@ -533,7 +517,7 @@ mc_kernel(const __grid_constant__ McParams p) {
         }
         if (k < kmax) one_step(k, false);
       }
-      if (G > 1 && !SPEC) __syncwarp();   // slots are rewritten by the next block
+      if (G > 1) __syncwarp();   // slots are rewritten by the next block
       B2_CLK(cb1);
       B2_ACC(3, cb0, cb1);
       // ---------------- histories: lane j writes the state of sample base+j+1 ---------
@@ -551,7 +535,7 @@ mc_kernel(const __grid_constant__ McParams p) {
       }
     }
 
-    if (kStaged && prepares) {
+    if (kStaged) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
@@ -562,7 +546,7 @@ mc_kernel(const __grid_constant__ McParams p) {
     if (p.n - 1 >= p.stats_start)
       proc_accumulate(st, p.ref_nav + (p.n - 1) * 9, pe_max, pe_sum, pe_sq, pe_k, pe_cnt);
   }
-  if (active && j == 0 && consumer) {
+  if (active && j == 0) {
     if (p.end_err) {
       const double* r = p.ref_nav + (p.n - 1) * 9;
       double* e = p.end_err + run * 9;
