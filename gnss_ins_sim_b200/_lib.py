@@ -100,6 +100,7 @@ SIGNATURES = {
 }
 
 _lib = None
+_load_error = None       # a failed build is not retried in the same process (every caller gets the same error)
 
 
 def lib_path():
@@ -108,17 +109,21 @@ def lib_path():
 
 def load():
     """Load libb2ins.so (building it first if nvcc is here and it is stale)."""
-    global _lib
+    global _lib, _load_error
     if _lib is not None:
         return _lib
+    if _load_error is not None:
+        raise B2insError(_load_error)
     path = lib_path()
     if _build.stale():          # missing, or built from other sources than the ones in this tree
         try:
             _build.build()
         except Exception as e:  # no nvcc on this box and no usable prebuilt library
             if not os.path.exists(path):
-                raise B2insError('libb2ins.so is missing and could not be built: %s' % e)
-            raise B2insError('libb2ins.so was built from other sources and could not be rebuilt: %s' % e)
+                _load_error = 'libb2ins.so is missing and could not be built: %s' % e
+            else:
+                _load_error = 'libb2ins.so was built from other sources and could not be rebuilt: %s' % e
+            raise B2insError(_load_error)
     elif _build.LAST_BUILD == 'not checked':
         _build.LAST_BUILD = 'reused'
     lib = ctypes.CDLL(path)
