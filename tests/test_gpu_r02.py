@@ -69,30 +69,36 @@ def test_every_launch_shape_matches_the_reference(gpu, rf, monkeypatch):
     monkeypatch.delenv('B2INS_MC_SHAPE')
 
 
-def test_ragged_run_counts_and_lengths_in_the_specialised_form(gpu):
+@pytest.mark.parametrize('rf', [1, 0])
+def test_ragged_run_counts_and_lengths_in_the_specialised_form(gpu, rf):
     """Run counts that do not fill the last CTA / lane group and series lengths that end inside a tile,
-    a round and a pass: same end-point errors as the single-warp form of the same experiment."""
+    a round, a pass and a speculative block of four steps: same end-point errors as the single-warp form
+    of the same experiment ('' = the default shape: the attitude / velocity split for groups of 4 and 8 in
+    ref_frame 1, the fused warp-specialised form otherwise)."""
     from gnss_ins_sim_b200 import engine
-    g = load_golden('philox_90deg_mid_rf1.npz')
+    g = load_golden('philox_90deg_mid_rf%d.npz' % rf)
     imu = _mid()
     nav = np.concatenate([g['ref_att'], g['ref_pos'], g['ref_vel']], axis=1)
-    for n in (1, 2, 7, 9, 129, 131, 777):
+    cases = [(1, 4, ''), (9, 4, ''), (33, 1, ''), (5, 8, ''), (3, 16, ''), (37, 2, ''),
+             (9, 4, '6,1,0'), (5, 8, '6,1,0'), (9, 4, '6,1,1')]
+    if rf == 1:
+        cases += [(9, 4, '6,2,0'), (5, 8, '6,2,0'), (1, 4, '6,2,0')]
+    for n in (1, 2, 4, 5, 7, 9, 129, 131, 777):
         dev = [engine.to_device(a) for a in (g['ref_gyro'][:n], g['ref_accel'][:n], nav[:n], g['ini'][None])]
-        for R, lanes, spec in ((1, 4, ''), (9, 4, ''), (33, 1, ''), (5, 8, ''), (3, 16, ''), (37, 2, ''),
-                               (9, 4, '6,2,0'), (5, 8, '6,2,0'), (1, 4, '6,2,0')):
+        for R, lanes, spec in cases:
             out = {}
             for shape in (spec, '0'):
                 if shape:
                     os.environ['B2INS_MC_SHAPE'] = shape
                 try:
-                    cfg = engine.make_mc_config(1, 100.0, n, R, 99, imu.gyro_err, imu.accel_err, 1, 9,
+                    cfg = engine.make_mc_config(rf, 100.0, n, R, 99, imu.gyro_err, imu.accel_err, 1, 9,
                                                 lanes_per_run=lanes, run_offset=1000)
                     out[shape] = engine.mc_free_integration(cfg, *dev, want_state=True)
                     out[shape] = (out[shape].end_err.cpu().numpy(), out[shape].end_state.cpu().numpy())
                 finally:
                     os.environ.pop('B2INS_MC_SHAPE', None)
-            assert np.abs(out[spec][0] - out['0'][0]).max() < 1e-11, (n, R, lanes, spec)
-            assert np.abs(out[spec][1] - out['0'][1]).max() < 1e-9 * 5e6, (n, R, lanes, spec)
+            assert np.abs(out[spec][0] - out['0'][0]).max() < 1e-11, (rf, n, R, lanes, spec)
+            assert np.abs(out[spec][1] - out['0'][1]).max() < 1e-9 * 5e6, (rf, n, R, lanes, spec)
 
 
 @pytest.mark.parametrize('rf', [1, 0])
