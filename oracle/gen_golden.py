@@ -197,6 +197,47 @@ def gen_philox(tag, motion, fs, accuracy, ref_frame, R, seed, env=None, run0=0):
                         **out, **extra)
 
 
+def gen_philox_config3(R=2, seed=11, stride=2000):
+    """BASELINE config 3 at its FULL length through the unmodified reference: motion_def-long_drive.csv
+    @200 Hz (193 036 samples), 'low-accuracy' IMU, ref_frame 0, R runs on the b2ins stream (run ids
+    0..R-1, as Sim(seed=...).run(R) names them).  Kept: the end-point state and error of every run and
+    the histories at every `stride`-th sample (the full arrays are 14 MB per run)."""
+    csv = os.path.join(MOTION, 'motion_def-long_drive.csv')
+    ini = read_ini(csv)
+    imu = fresh_imu('low-accuracy')
+    fs = 200.0
+    algo = free_integration.FreeIntegration(ini)
+    sim = ins_sim.Sim([fs, 0.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=algo)
+    probe = ins_sim.Sim([fs, 0.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=None)
+    real_randn, real_rand = np.random.randn, np.random.rand
+    np.random.randn = lambda *s: np.zeros(s)
+    try:
+        probe.run(1)
+    finally:
+        np.random.randn = real_randn
+    n = probe.dmgr.time.data.shape[0]
+    run_ids = np.arange(R)
+    q = RandnQueue()
+    inject_stream(q, n, run_ids, seed)
+    np.random.randn = q
+    try:
+        sim.run(R)
+    finally:
+        np.random.randn, np.random.rand = real_randn, real_rand
+    assert not q.q, 'unused queued normals: %d' % len(q.q)
+    d = sim.dmgr
+    att = np.stack([d.att_euler.data['algo0_%d' % i] for i in range(R)])
+    pos = np.stack([d.pos.data['algo0_%d' % i] for i in range(R)])
+    vel = np.stack([d.vel.data['algo0_%d' % i] for i in range(R)])
+    end_state = np.concatenate([att[:, -1], pos[:, -1], vel[:, -1]], axis=1)
+    ref_end = np.concatenate([d.ref_att_euler.data[-1], d.ref_pos.data[-1], d.ref_vel.data[-1]])
+    np.savez_compressed(os.path.join(OUT, 'philox_config3_long_drive_rf0.npz'),
+                        fs=fs, n=n, seed=seed, run_ids=run_ids, ini=ini, stride=stride,
+                        end_state=end_state, ref_end=ref_end,
+                        att=att[:, ::stride], pos=pos[:, ::stride], vel=vel[:, ::stride],
+                        ref_pos=d.ref_pos.data[::stride], ref_att=d.ref_att_euler.data[::stride])
+
+
 def gen_ned_stats(R=8, seed=12345):
     """get_error_stats('pos', extra_opt='ned' | 'ecef') of the reference (ins_data_manager.py:543-552)
     for the philox_90deg_mid_rf0 experiment: LLA end-point errors in metres, in the local NED frame or
@@ -465,6 +506,23 @@ def gen_allan():
                         fs2=50.0, x2=x2, avar2=avar2, tau2=tau2, x3=x3)
 
 
+def gen_allan_config4(n=14400000, fs=400.0, seed=5, run=2):
+    """BASELINE config 4 at its FULL length: allan.allan_var of the unmodified reference on ONE 14.4 M-sample
+    series (10 h @400 Hz): the gyro-z and accel-x measurements of run `run` of a static 'low-accuracy' IMU
+    on the b2ins stream (made by the C oracle's generator -- any input would do, this is the one the
+    config-4 tests already produce).  Kept: tau and the two Allan variances (55 values each)."""
+    import oracle_c
+    imu = fresh_imu('low-accuracy')
+    ref_gyro = np.zeros((n, 3))
+    ref_accel = np.tile(np.array([4.9, 0.0, -8.487]), (n, 1))        # 30 deg pitch, static
+    og, oa = oracle_c.imu_noise(fs, ref_gyro, ref_accel, imu.gyro_err, imu.accel_err, seed, [run])
+    avar_g, tau = allan.allan_var(np.ascontiguousarray(og[0, :, 2]), fs)
+    avar_a, tau_a = allan.allan_var(np.ascontiguousarray(oa[0, :, 0]), fs)
+    assert np.array_equal(tau, tau_a)
+    np.savez_compressed(os.path.join(OUT, 'allan_config4_full_length.npz'), n=n, fs=fs, seed=seed, run=run,
+                        tau=tau, avar_gyro_z=avar_g, avar_accel_x=avar_a)
+
+
 def gen_psd():
     tab = np.genfromtxt(os.path.join(MOTION, 'vib_psd.csv'), delimiter=',', skip_header=1)
     rng = np.random.RandomState(7)
@@ -508,6 +566,7 @@ def main():
                778, env={'acc': '[0.03 0.001 0.01]g-3Hz-sinusoidal',
                          'gyro': '[6 5 4]d-0.5Hz-sinusoidal'})
     gen_ned_stats()
+    gen_philox_config3()
     gen_philox_white_drift(1)
     gen_philox_white_drift(0)
     gen_philox_psd(1)
@@ -519,6 +578,7 @@ def main():
     gen_traj('90deg_turn_100hz_rf0', 'motion_def-90deg_turn.csv', 100.0, 0)
     gen_pathgen()
     gen_allan()
+    gen_allan_config4()
     gen_psd()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -200,6 +200,15 @@ def test_config4_length_allan_through_sim(eng):
     av, _ = oracle_c.allan_var(np.ascontiguousarray(oa[0, :, 0]), fs)
     assert_close(ada['algo0_2'][:, 0], np.sqrt(av), 1e-8, 0.0, 'ad_accel x')
     assert_close(t, ot, 1e-12, 0.0, 'tau')
+    # ... and against the unmodified reference's allan_var on the same series (oracle/gen_golden.py:
+    # gen_allan_config4; same seed, run and IMU as here)
+    from conftest import load_golden
+    ref = load_golden('allan_config4_full_length.npz')
+    assert int(ref['n']) == n and int(ref['seed']) == seed and int(ref['run']) == 2
+    assert_close(t, ref['tau'], 1e-12, 0.0, 'tau (reference)')
+    assert_close(adg['algo0_2'][:, 2], np.sqrt(ref['avar_gyro_z']), 1e-8, 0.0, 'ad_gyro z (reference)')
+    # (accel x rides on a 4.9 m/s^2 offset: summation order shows at 1e-8 of the variance)
+    assert_close(ada['algo0_2'][:, 0], np.sqrt(ref['avar_accel_x']), 1e-6, 0.0, 'ad_accel x (reference)')
     # white-noise regime (tau << bias correlation time): AD(tau) = arw / sqrt(tau)
     arw = LOW_G['arw'][0]
     k = np.where((t >= 0.01) & (t <= 1.0))[0]
@@ -247,3 +256,37 @@ def test_k1_time_segmented_path(eng):
     og, oa = oracle_c.imu_noise(fs, gyro, accel, fast_g, LOW_A, 3, np.arange(40, 40 + R))
     assert_close(g.cpu().numpy(), og, 1e-11, 1.0, 'gyro')
     assert_close(a.cpu().numpy(), oa, 1e-11, 1.0, 'accel')
+
+
+def test_config3_full_length_against_the_reference(eng):
+    """BASELINE config 3 at its full length against the UNMODIFIED REFERENCE: motion_def-long_drive.csv
+    @200 Hz (193 036 samples), 'low-accuracy' IMU, ref_frame 0 through Sim -- end points and the histories
+    at every 2000th sample against what the reference reached with the same injected normals
+    (philox_config3_long_drive_rf0.npz, oracle/gen_golden.py: gen_philox_config3)."""
+    import os
+    from conftest import ROOT, load_golden, wrap_pi
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import Sim
+    from gnss_ins_sim_b200.free_integration import FreeIntegration
+    g = load_golden('philox_config3_long_drive_rf0.npz')
+    csv = os.path.join(ROOT, 'tests', 'golden', 'motion_def-long_drive.csv')
+    imu = imu_model.IMU(accuracy='low-accuracy', axis=6, gps=False)
+    R, stride = len(g['run_ids']), int(g['stride'])
+    sim = Sim([float(g['fs']), 0.0, 0.0], csv, ref_frame=0, imu=imu, algorithm=FreeIntegration(g['ini']),
+              seed=int(g['seed']))
+    sim.run(R)
+    assert sim._traj['ref_gyro'].shape[0] == int(g['n'])
+    want = g['end_state'] - g['ref_end'][None]
+    want[:, 0:3] = wrap_pi(want[:, 0:3])
+    err = sim.end_point_errors()
+    # contract 1e-6 relative (the end points are ~1e3 m and ~30 m/s off the truth after 965 s)
+    assert np.abs(wrap_pi(err[:, 0:3] - want[:, 0:3])).max() < 1e-9
+    assert np.abs(err[:, 6:9] - want[:, 6:9]).max() < 1e-5
+    assert np.abs((err[:, 3:5] - want[:, 3:5]) * 6.4e6).max() < 1e-3 and np.abs(err[:, 5] - want[:, 5]).max() < 1e-3
+    h = sim.histories(stride=stride)
+    att, pos, vel = (np.asarray(h[k]) for k in ('att_euler', 'pos', 'vel'))       # [R, rows, 3] host arrays
+    m = g['att'].shape[1]
+    assert np.abs(wrap_pi(att[:, :m] - g['att'])).max() < 1e-9
+    assert np.abs(vel[:, :m] - g['vel']).max() < 1e-5
+    assert np.abs((pos[:, :m, 0:2] - g['pos'][:, :, 0:2]) * 6.4e6).max() < 1e-3
+    assert np.abs(pos[:, :m, 2] - g['pos'][:, :, 2]).max() < 1e-3

@@ -194,3 +194,53 @@ def test_psd_vibration_through_the_reference_sim_is_pinned():
                             for c in range(3)], axis=1)
             mea = onp.sensor_gen(fs, ref, err, key, zg[r:r + 1], zw[r:r + 1], vib=vib[None])[0]
             assert_close(mea, out[r], 1e-11, what='sensor %d run %d' % (sensor, r))
+
+
+def test_config3_full_length_oracle_against_the_reference():
+    """BASELINE config 3 at its full length (193 036 samples @200 Hz, 'low-accuracy', ref_frame 0): the
+    C oracle on the host path generator's trajectory against the end points the unmodified reference
+    reached on its own trajectory with the same injected normals (philox_config3_long_drive_rf0.npz)."""
+    import os
+    import oracle_c
+    from conftest import ROOT
+    from gnss_ins_sim_b200 import imu_model
+    from gnss_ins_sim_b200.sim import trajectory_from_motion_def
+    g = load_golden('philox_config3_long_drive_rf0.npz')
+    csv = os.path.join(ROOT, 'tests', 'golden', 'motion_def-long_drive.csv')
+    t = trajectory_from_motion_def(float(g['fs']), csv, 0)
+    n = int(g['n'])
+    assert t['ref_gyro'].shape == (n, 3)
+    nav_end = np.concatenate([t['ref_att'][-1], t['ref_pos'][-1], t['ref_vel'][-1]])
+    # the two trajectories agree row by row (tests/test_cpu_host.py); their last rows here
+    assert np.abs(wrap_pi(nav_end[0:3] - g['ref_end'][0:3])).max() < 1e-11
+    assert np.abs(nav_end[3:5] - g['ref_end'][3:5]).max() < 1e-13 and abs(nav_end[5] - g['ref_end'][5]) < 1e-6
+    imu = imu_model.IMU(accuracy='low-accuracy', axis=6, gps=False)
+    R = len(g['run_ids'])
+    err, _ = oracle_c.mc_free_integration(0, float(g['fs']), R, int(g['run_ids'][0]), t['ref_gyro'], t['ref_accel'],
+                                          nav_end, imu.gyro_err, imu.accel_err, int(g['seed']), g['ini'][None],
+                                          threads=0)
+    want = g['end_state'] - g['ref_end'][None]
+    want[:, 0:3] = wrap_pi(want[:, 0:3])
+    # the contract is 1e-6 relative; after 1.9e5 steps the end points are ~1e3 m / 30 m/s off the truth
+    assert np.abs(wrap_pi(err[:, 0:3] - want[:, 0:3])).max() < 1e-9
+    assert np.abs(err[:, 6:9] - want[:, 6:9]).max() < 1e-6
+    assert np.abs((err[:, 3:5] - want[:, 3:5]) * 6.4e6).max() < 1e-4 and np.abs(err[:, 5] - want[:, 5]).max() < 1e-4
+
+
+def test_config4_full_length_allan_oracle_against_the_reference():
+    """BASELINE config 4 at its full length (14.4 M samples @400 Hz): the C oracle's allan_var against
+    allan.allan_var of the unmodified reference on the same series (allan_config4_full_length.npz)."""
+    import oracle_c
+    from gnss_ins_sim_b200 import imu_model
+    g = load_golden('allan_config4_full_length.npz')
+    n, fs = int(g['n']), float(g['fs'])
+    imu = imu_model.IMU(accuracy='low-accuracy', axis=6, gps=False)
+    ref_gyro = np.zeros((n, 3))
+    ref_accel = np.tile(np.array([4.9, 0.0, -8.487]), (n, 1))
+    og, oa = oracle_c.imu_noise(fs, ref_gyro, ref_accel, imu.gyro_err, imu.accel_err, int(g['seed']), [int(g['run'])])
+    av, tau = oracle_c.allan_var(np.ascontiguousarray(og[0, :, 2]), fs)
+    assert_close(tau, g['tau'], 1e-12, 0.0, 'tau')
+    assert_close(av, g['avar_gyro_z'], 1e-10, 0.0, 'avar gyro z')
+    av, _ = oracle_c.allan_var(np.ascontiguousarray(oa[0, :, 0]), fs)
+    # (a 4.9 m/s^2 offset under increments of 1e-4: the bin means cancel to ~1e-17 absolute either way)
+    assert_close(av, g['avar_accel_x'], 1e-7, 0.0, 'avar accel x')
