@@ -161,13 +161,9 @@ def host_ptr(a):
 
 def sensor_err(err, white_key):
     """imu_model-style dict {'b','b_drift','b_corr',white_key} -> SensorErr."""
-    s = SensorErr()
-    for c in range(3):
-        s.b[c] = float(err['b'][c])
-        s.b_drift[c] = float(err['b_drift'][c])
-        s.b_corr[c] = float(err['b_corr'][c])
-        s.rw[c] = float(err[white_key][c])
-    return s
+    a = np.array([err['b'], err['b_drift'], err['b_corr'], err[white_key]], dtype=np.float64)   # [4][3] = the struct
+    assert a.shape == (4, 3)
+    return SensorErr.from_buffer_copy(a)
 
 
 def vib(vib_def, series_ptr=None, series_len=0):

@@ -28,6 +28,8 @@ def world():
 def shard(total, r=None, w=None):
     """Contiguous block [lo, hi) of `total` runs owned by rank r of w (first ranks take the
     remainder).  Global run ids are rank-independent, so results do not depend on w."""
+    if r is None and w is None and not initialised():
+        return 0, int(total)
     r = rank() if r is None else r
     w = world() if w is None else w
     base, rem = divmod(int(total), w)
