@@ -166,14 +166,13 @@ McShape default_shape(int G, int rf) {
 
 // Lanes per run.  The recurrence is serial in time, so the only parallelism is across runs (and,
 // for the noise, across the samples and channels the producers take).  One integrator warp needs
-// ~370 cycles per step (ref_frame 1) whatever the number of runs it carries -- the dependent-issue
-// latency of a single warp -- so with few runs the narrowest group that still gives every SM a CTA
-// wins: fewer replicated lanes, one producer pass per G steps.  With many runs G = 1 is the throughput
-// form, and beyond ~2.6e5 runs the single-warp kernel (every warp generates and integrates, five CTAs
-// per SM) overtakes the specialised one.  Measured on B200 (profiles/spec2_probe_r02.jsonl, run-steps/s
-// at n = 1000, ref_frame 1): 500 runs G = 8 3.1e9; 1000 runs G = 4 5.4e9; 2000 / 4000 runs G = 2
-// 6.6e9 / 9.2e9; 8000 / 40 000 / 100 000 runs G = 1 1.06e10 / 1.22e10 / 1.27e10; 10^6 runs single-warp
-// form 1.79e10.
+// ~350 cycles per step (ref_frame 1; its attitude half alone ~273) whatever the number of runs it carries
+// -- the dependent-issue latency of a single warp -- so with few runs the narrowest group that still gives
+// every SM a CTA wins: fewer replicated lanes, fewer producer jobs per step.  With many runs G = 1 is the
+// throughput form, and beyond ~2.6e5 runs the single-warp kernel (every warp generates and integrates, five
+// CTAs per SM) overtakes the specialised one.  Measured on B200 (profiles/spec2_probe_r02.jsonl and
+// kernel_bench_r02.jsonl, run-steps/s at n = 1000, ref_frame 1): 500 runs G = 8 3.4e9; 1000 runs G = 4
+// 6.0e9; 2000 runs G = 2 6.9e9; 100 000 runs G = 1 1.37e10; 10^6 runs single-warp form 1.95e10.
 // spec_ok: the launch can take the warp-specialised form (fused noise, end-point statistics only)
 constexpr int64_t kSpecMaxRunsG1 = int64_t(1) << 18;
 

@@ -1,18 +1,18 @@
 // K12, ref_frame 1, few runs: the STEP ITSELF split over two warps.
 //
-// With 1000 runs a B200 has one integrator warp per SM, and that warp needs ~370 cycles per step:
-// ~110 instructions on dependency chains at 8.8 cycles per dependent FP64 issue.  In the
-// virtual inertial frame the attitude recurrence does not read velocity or position
+// With 1000 runs a B200 has one integrator warp per SM, and that warp needs ~350 cycles per step: ~120
+// instructions, most of them FP64, on dependency chains at 8.8 cycles per dependent issue.
+// In the virtual inertial frame the attitude recurrence does not read velocity or position
 // (free_integration.py:104), so it runs ahead in its own warp and hands the sin/cos of every step
 // through a shared-memory ring to a second warp that does velocity and position (:109-116):
 //
-//   producers (6 warps, one channel each)  --slots-->  A: rates, three rotations, 1/cos
-//                                           \--slots-->  V: c_bn g, w x v, v_b, v = c_bn^T v_b, pos   <--ring-- A
+//   producers (one job = a channel of four runs x 8 samples)  --slots-->  A: rates, three rotations, 1/cos
+//                                                              \--slots-->  V: c_bn g, w x v, v_b, v = c_bn^T v_b, pos   <--ring-- A
 //
 // One named barrier per round of kAvRound samples couples the three stages: in interval i the
 // producers fill round i, A integrates round i-1, V round i-2 (slots triple-buffered, the ring
-// double-buffered).  A sits alone on SM sub-partition 0; V shares sub-partition 1 with two producers, the
-// other four share 2 and 3 (CTA of 12 warps, four of which leave at once).
+// double-buffered).  A (~273 cycles per step alone) is the critical path; the warp placement is in the
+// role tables below.
 #pragma once
 #include "mc_spec_kernel.cuh"
 

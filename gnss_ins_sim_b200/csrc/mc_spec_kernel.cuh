@@ -18,7 +18,8 @@
 //     of 32 (1 + P) threads per round of kRound samples, slots double-buffered so that the producers
 //     fill round r + 1 while round r is integrated.
 //
-// Which (G, P, WI) is used for how many runs is measured, not guessed: b2ins_api.cu, spec_choice().
+// Which (G, P, WI) is used for how many runs is measured, not guessed: b2ins_api.cu, auto_lanes() and
+// default_shape() (ref_frame 1 with groups of 4 and 8 lanes takes mc_av_kernel.cuh instead).
 #pragma once
 #include "mc_kernel.cuh"
 
